@@ -1,0 +1,366 @@
+// C-ABI of aqlm_b200 (see include/aqlm_b200.h): argument validation, kernel selection, launches.
+// The host-side role of the reference's cuda_kernel.cpp (dtype check 9-25, group-size switch 113-146,
+// launch heuristics cuda_kernel.cu:476-516) without torch types.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "dequant.cuh"
+#include "gemv.cuh"
+
+namespace aqlm_b200 {
+
+std::atomic<uint64_t> g_launch_count{0};
+
+const DeviceInfo* device_info() {
+  static DeviceInfo infos[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    fail(AQLM_B200_ERR_CUDA, "cudaGetDevice failed (no CUDA device / driver?)");
+    return nullptr;
+  }
+  DeviceInfo& d = infos[dev];
+  if (!d.ok) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!d.ok) {
+      cudaError_t e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      if (e != cudaSuccess) {
+        fail(AQLM_B200_ERR_CUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+        return nullptr;
+      }
+      d.ok = true;
+    }
+  }
+  if (d.cc_major != 10) {
+    fail(AQLM_B200_ERR_ARCH, "aqlm_b200 is built for sm_100a only; device %d is sm_%d%d", dev, d.cc_major, d.cc_minor);
+    return nullptr;
+  }
+  return &d;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+static int validate(const aqlm_b200_weight_t* w, bool need_scales) {
+  if (!w) return fail(AQLM_B200_ERR_SHAPE, "weight descriptor is NULL");
+  if (w->dtype != AQLM_B200_F16 && w->dtype != AQLM_B200_BF16)
+    return fail(AQLM_B200_ERR_DTYPE,
+                "AQLM CUDA kernels only support float16 and bfloat16. Please specify the correct `torch_dtype` "
+                "when loading the model.");
+  if (w->out_group_size != 1)
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "aqlm_b200 kernels require out_group_size == 1, got %d", w->out_group_size);
+  if (w->in_group_size != 8 && w->in_group_size != 16)
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "AQLM CUDA kernels only support codebooks with 8 or 16 features. Got %d.",
+                w->in_group_size);
+  if (w->nbits_per_codebook < 1 || w->nbits_per_codebook > 16)
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "nbits_per_codebook must be in [1,16], got %d", w->nbits_per_codebook);
+  if (w->num_codebooks < 1 || w->num_codebooks > 16)
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "num_codebooks must be in [1,16], got %d", w->num_codebooks);
+  if (w->in_features <= 0 || w->out_features <= 0 || w->in_features % w->in_group_size != 0)
+    return fail(AQLM_B200_ERR_SHAPE, "bad shape: in_features=%lld out_features=%lld in_group_size=%d",
+                (long long)w->in_features, (long long)w->out_features, w->in_group_size);
+  if (w->in_features > (1ll << 30) || w->out_features > (1ll << 30))
+    return fail(AQLM_B200_ERR_SHAPE, "dimension too large");
+  if (!w->codes || !w->codebooks) return fail(AQLM_B200_ERR_SHAPE, "codes/codebooks pointer is NULL");
+  if (need_scales && !w->scales) return fail(AQLM_B200_ERR_SHAPE, "scales pointer is NULL");
+  if ((reinterpret_cast<uintptr_t>(w->codebooks) & 15) != 0)
+    return fail(AQLM_B200_ERR_SHAPE, "codebooks must be 16-byte aligned");
+  return AQLM_B200_OK;
+}
+
+template <typename KernelT>
+static int set_smem(KernelT kernel, size_t smem) {
+  if (smem > 48 * 1024) AQLM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return AQLM_B200_OK;
+}
+
+template <typename T, int K, int CB, int G, int BT, bool CBS, int GM>
+static int launch_vec(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
+  const size_t smem = (size_t)BT * p.in_features * 2 + (CBS ? ((size_t)K << p.nbits) * G * 2 : 0);
+  auto kernel = gemv_vec_kernel<T, K, CB, G, BT, CBS, GM>;
+  static std::atomic<size_t> configured{0};
+  if (configured.load(std::memory_order_relaxed) < smem) {
+    int rc = set_smem(kernel, smem);
+    if (rc) return rc;
+    configured.store(smem, std::memory_order_relaxed);
+  }
+  int per_sm = (int)((size_t)di->max_smem_optin / (smem + 1024));
+  const int max_per_sm = env_int("AQLM_B200_GEMV_CTAS_PER_SM", 8);
+  if (per_sm > max_per_sm) per_sm = max_per_sm;
+  if (per_sm < 1) per_sm = 1;
+  int blocks = (p.out_features + 7) / 8;
+  if (blocks > di->sm_count * per_sm) blocks = di->sm_count * per_sm;
+  kernel<<<blocks, kGemvThreads, smem, st>>>(p);
+  count_launch();
+  AQLM_CUDA_CHECK(cudaGetLastError());
+  return AQLM_B200_OK;
+}
+
+template <typename T, int CB, int G, int BT>
+static int launch_generic(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
+  int blocks = (p.out_features + 7) / 8;
+  if (blocks > di->sm_count * 8) blocks = di->sm_count * 8;
+  gemv_generic_kernel<T, CB, G, BT><<<blocks, kGemvThreads, 0, st>>>(p);
+  count_launch();
+  AQLM_CUDA_CHECK(cudaGetLastError());
+  return AQLM_B200_OK;
+}
+
+template <typename T, int BT>
+static int dispatch_bt(const aqlm_b200_weight_t* w, const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
+  const int K = w->num_codebooks, nbits = w->nbits_per_codebook, G = w->in_group_size;
+  const int code_bytes = nbits <= 8 ? 1 : 2;
+  const size_t row_bytes = (size_t)p.in_groups * K * code_bytes;
+  const bool vec_ok = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(w->codes) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) && !env_int("AQLM_B200_FORCE_GENERIC", 0);
+  const size_t x_smem = (size_t)BT * p.in_features * 2;
+  const size_t budget = (size_t)di->max_smem_optin - 2048;
+  if (vec_ok && nbits == 16 && K == 1 && x_smem <= budget) {
+    const int gm = env_int("AQLM_B200_GATHER_MODE", 0);
+    if (G == 8) {
+      if (gm == 1) return launch_vec<T, 1, 2, 8, BT, false, 1>(p, di, st);
+      if (gm == 2) return launch_vec<T, 1, 2, 8, BT, false, 2>(p, di, st);
+      return launch_vec<T, 1, 2, 8, BT, false, 0>(p, di, st);
+    }
+    return launch_vec<T, 1, 2, 16, BT, false, 0>(p, di, st);
+  }
+  if (vec_ok && nbits == 8 && G == 8 && x_smem + (size_t)K * 4096 <= budget) {
+    if (K == 1) return launch_vec<T, 1, 1, 8, BT, true, 0>(p, di, st);
+    if (K == 2) return launch_vec<T, 2, 1, 8, BT, true, 0>(p, di, st);
+    if (K == 4) return launch_vec<T, 4, 1, 8, BT, true, 0>(p, di, st);
+    if (K == 8) return launch_vec<T, 8, 1, 8, BT, true, 0>(p, di, st);
+  }
+  if (code_bytes == 2) {
+    if (G == 8) return launch_generic<T, 2, 8, BT>(p, di, st);
+    return launch_generic<T, 2, 16, BT>(p, di, st);
+  }
+  if (G == 8) return launch_generic<T, 1, 8, BT>(p, di, st);
+  return launch_generic<T, 1, 16, BT>(p, di, st);
+}
+
+template <typename T>
+static int matmat_typed(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, uint32_t flags,
+                        const DeviceInfo* di, cudaStream_t st) {
+  const bool partial = (flags & AQLM_B200_FLAG_PARTIAL_F32) != 0;
+  GemvParams p;
+  p.codes = w->codes;
+  p.codebooks = w->codebooks;
+  p.scales = w->scales;
+  p.bias = w->bias;
+  p.out_features = (int)w->out_features;
+  p.in_features = (int)w->in_features;
+  p.in_groups = (int)(w->in_features / w->in_group_size);
+  p.nbits = w->nbits_per_codebook;
+  p.num_codebooks = w->num_codebooks;
+  p.partial_f32 = partial ? 1 : 0;
+  const size_t out_elt = partial ? 4 : 2;
+  // largest pass size whose x tile fits in shared memory
+  int max_bt = 8;
+  while (max_bt > 1 && (size_t)max_bt * w->in_features * 2 + 40 * 1024 > (size_t)di->max_smem_optin) max_bt >>= 1;
+  for (int64_t b0 = 0; b0 < batch; b0 += max_bt) {
+    const int nb = (int)((batch - b0) < max_bt ? (batch - b0) : max_bt);
+    p.batch = nb;
+    p.x = reinterpret_cast<const uint8_t*>(input) + (size_t)b0 * w->in_features * 2;
+    p.y = reinterpret_cast<uint8_t*>(output) + (size_t)b0 * w->out_features * out_elt;
+    int rc;
+    if (nb == 1) rc = dispatch_bt<T, 1>(w, p, di, st);
+    else if (nb == 2) rc = dispatch_bt<T, 2>(w, p, di, st);
+    else if (nb <= 4) rc = dispatch_bt<T, 4>(w, p, di, st);
+    else rc = dispatch_bt<T, 8>(w, p, di, st);
+    if (rc) return rc;
+  }
+  return AQLM_B200_OK;
+}
+
+template <typename T>
+static int dequant_typed(const aqlm_b200_weight_t* w, void* out, int apply_scales, cudaStream_t st) {
+  const int in_groups = (int)(w->in_features / w->in_group_size);
+  const int64_t n = w->out_features * in_groups;
+  const int threads = 256;
+  const int64_t blocks = (n + threads - 1) / threads;
+  if (blocks > 0x7fffffffll) return fail(AQLM_B200_ERR_SHAPE, "weight too large for one dequant launch");
+  const T* sc = apply_scales ? reinterpret_cast<const T*>(w->scales) : nullptr;
+  const int cb = w->nbits_per_codebook <= 8 ? 1 : 2;
+#define AQLM_DQ(CB, G)                                                                                        \
+  dequant_kernel<T, CB, G><<<(unsigned)blocks, threads, 0, st>>>(w->codes, w->codebooks, sc, out,            \
+                                                                   w->out_features, in_groups, w->num_codebooks, \
+                                                                   w->nbits_per_codebook)
+  if (cb == 2 && w->in_group_size == 8) AQLM_DQ(2, 8);
+  else if (cb == 2) AQLM_DQ(2, 16);
+  else if (w->in_group_size == 8) AQLM_DQ(1, 8);
+  else AQLM_DQ(1, 16);
+#undef AQLM_DQ
+  count_launch();
+  AQLM_CUDA_CHECK(cudaGetLastError());
+  return AQLM_B200_OK;
+}
+
+static aqlm_b200_weight_t make_weight(const void* codes, const void* codebooks, const void* scales, const void* bias,
+                                      int64_t in_features, int64_t out_features, int K, int nbits, int g, int dtype) {
+  aqlm_b200_weight_t w;
+  memset(&w, 0, sizeof(w));
+  w.codes = codes;
+  w.codebooks = codebooks;
+  w.scales = scales;
+  w.bias = bias;
+  w.in_features = in_features;
+  w.out_features = out_features;
+  w.num_codebooks = K;
+  w.nbits_per_codebook = nbits;
+  w.in_group_size = g;
+  w.out_group_size = 1;
+  w.dtype = dtype;
+  return w;
+}
+
+}  // namespace aqlm_b200
+
+using namespace aqlm_b200;
+
+extern "C" {
+
+int aqlm_b200_version(void) { return AQLM_B200_VERSION; }
+const char* aqlm_b200_last_error(void) { return tls_error_buf(); }
+uint64_t aqlm_b200_launch_count(void) { return g_launch_count.load(); }
+
+int aqlm_b200_matmat_ex(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, uint32_t flags,
+                        void* stream) {
+  const bool partial = (flags & AQLM_B200_FLAG_PARTIAL_F32) != 0;
+  int rc = validate(w, !partial);
+  if (rc) return rc;
+  if (!input || !output) return fail(AQLM_B200_ERR_SHAPE, "input/output pointer is NULL");
+  if (batch < 0) return fail(AQLM_B200_ERR_SHAPE, "negative batch");
+  if (batch == 0) return AQLM_B200_OK;
+  const DeviceInfo* di = device_info();
+  if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (w->dtype == AQLM_B200_F16) return matmat_typed<__half>(w, input, output, batch, flags, di, st);
+  return matmat_typed<__nv_bfloat16>(w, input, output, batch, flags, di, st);
+}
+
+int aqlm_b200_matmat(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, void* stream) {
+  return aqlm_b200_matmat_ex(w, input, output, batch, 0, stream);
+}
+
+int aqlm_b200_matmat_dequant(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch,
+                             void* stream) {
+  // v0: batch processed in passes of 8 rows through the fused gather+dequant+dot kernel (weights are
+  // re-gathered per pass).  To be replaced by the tcgen05 fused dequant+GEMM.
+  return aqlm_b200_matmat_ex(w, input, output, batch, 0, stream);
+}
+
+int aqlm_b200_dequant(const aqlm_b200_weight_t* w, void* weight_out, int apply_scales, void* stream) {
+  int rc = validate(w, apply_scales != 0);
+  if (rc) return rc;
+  if (!weight_out || (reinterpret_cast<uintptr_t>(weight_out) & 15))
+    return fail(AQLM_B200_ERR_SHAPE, "weight_out must be a 16-byte aligned device pointer");
+  if (!device_info()) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (w->dtype == AQLM_B200_F16) return dequant_typed<__half>(w, weight_out, apply_scales, st);
+  return dequant_typed<__nv_bfloat16>(w, weight_out, apply_scales, st);
+}
+
+int aqlm_b200_matmat_dequant_transposed(const aqlm_b200_weight_t* w, const void* grad_output, void* grad_input,
+                                        int64_t batch, void* workspace, void* stream) {
+  (void)w; (void)grad_output; (void)grad_input; (void)batch; (void)workspace; (void)stream;
+  return fail(AQLM_B200_ERR_UNSUPPORTED, "matmat_dequant_transposed (backward) is not implemented yet (SURVEY §8f.3)");
+}
+
+int aqlm_b200_scale_bias(const float* partial, const void* scales, const void* bias, void* output, int64_t batch,
+                         int64_t out_features, int32_t dtype, void* stream) {
+  if (!partial || !scales || !output) return fail(AQLM_B200_ERR_SHAPE, "NULL pointer");
+  if (dtype != AQLM_B200_F16 && dtype != AQLM_B200_BF16) return fail(AQLM_B200_ERR_DTYPE, "dtype must be f16/bf16");
+  if (batch <= 0 || out_features <= 0) return AQLM_B200_OK;
+  if (!device_info()) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t n = batch * out_features;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dtype == AQLM_B200_F16)
+    scale_bias_kernel<__half><<<blocks, 256, 0, st>>>(partial, (const __half*)scales, (const __half*)bias,
+                                                      (__half*)output, batch, out_features);
+  else
+    scale_bias_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(partial, (const __nv_bfloat16*)scales,
+                                                             (const __nv_bfloat16*)bias, (__nv_bfloat16*)output, batch,
+                                                             out_features);
+  count_launch();
+  AQLM_CUDA_CHECK(cudaGetLastError());
+  return AQLM_B200_OK;
+}
+
+int aqlm_b200_matmat_host(const aqlm_b200_weight_t* w, const void* input_host, void* output_host, void* input_dev,
+                          void* output_dev, int64_t batch, void* stream) {
+  int rc = validate(w, true);
+  if (rc) return rc;
+  if (!input_host || !output_host || !input_dev || !output_dev) return fail(AQLM_B200_ERR_SHAPE, "NULL buffer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  AQLM_CUDA_CHECK(cudaMemcpyAsync(input_dev, input_host, (size_t)batch * w->in_features * 2, cudaMemcpyHostToDevice, st));
+  rc = aqlm_b200_matmat_ex(w, input_dev, output_dev, batch, 0, stream);
+  if (rc) return rc;
+  AQLM_CUDA_CHECK(cudaMemcpyAsync(output_host, output_dev, (size_t)batch * w->out_features * 2, cudaMemcpyDeviceToHost, st));
+  AQLM_CUDA_CHECK(cudaStreamSynchronize(st));
+  return AQLM_B200_OK;
+}
+
+// ---- flat wrappers ------------------------------------------------------------------------------
+#define AQLM_FLAT_MATMAT(NAME, K, NBITS, GEXPR, FN)                                                               \
+  aqlm_b200_weight_t w = make_weight(codes, codebooks, scales, bias, in_features, out_features, K, NBITS, GEXPR, dtype); \
+  return FN(&w, input, output, batch, stream)
+
+int aqlm_b200_code1x16_matmat(const void* input, const void* codes, const void* codebooks, const void* scales,
+                              const void* bias, void* output, int64_t batch, int64_t in_features,
+                              int64_t out_features, int32_t in_group_size, int32_t dtype, void* stream) {
+  AQLM_FLAT_MATMAT(code1x16_matmat, 1, 16, in_group_size, aqlm_b200_matmat);
+}
+int aqlm_b200_code2x8_matmat(const void* input, const void* codes, const void* codebooks, const void* scales,
+                             const void* bias, void* output, int64_t batch, int64_t in_features,
+                             int64_t out_features, int32_t dtype, void* stream) {
+  AQLM_FLAT_MATMAT(code2x8_matmat, 2, 8, 8, aqlm_b200_matmat);
+}
+int aqlm_b200_code1x8_matmat(const void* input, const void* codes, const void* codebooks, const void* scales,
+                             const void* bias, void* output, int64_t batch, int64_t in_features,
+                             int64_t out_features, int32_t dtype, void* stream) {
+  AQLM_FLAT_MATMAT(code1x8_matmat, 1, 8, 8, aqlm_b200_matmat);
+}
+int aqlm_b200_code1x16_matmat_dequant(const void* input, const void* codes, const void* codebooks,
+                                      const void* scales, const void* bias, void* output, int64_t batch,
+                                      int64_t in_features, int64_t out_features, int32_t in_group_size,
+                                      int32_t dtype, void* stream) {
+  AQLM_FLAT_MATMAT(code1x16_matmat_dequant, 1, 16, in_group_size, aqlm_b200_matmat_dequant);
+}
+int aqlm_b200_code2x8_matmat_dequant(const void* input, const void* codes, const void* codebooks,
+                                     const void* scales, const void* bias, void* output, int64_t batch,
+                                     int64_t in_features, int64_t out_features, int32_t dtype, void* stream) {
+  AQLM_FLAT_MATMAT(code2x8_matmat_dequant, 2, 8, 8, aqlm_b200_matmat_dequant);
+}
+int aqlm_b200_code1x8_matmat_dequant(const void* input, const void* codes, const void* codebooks,
+                                     const void* scales, const void* bias, void* output, int64_t batch,
+                                     int64_t in_features, int64_t out_features, int32_t dtype, void* stream) {
+  AQLM_FLAT_MATMAT(code1x8_matmat_dequant, 1, 8, 8, aqlm_b200_matmat_dequant);
+}
+#undef AQLM_FLAT_MATMAT
+
+int aqlm_b200_code1x16_dequant(const void* codes, const void* codebooks, const void* scales, void* weight_out,
+                               int64_t in_features, int64_t out_features, int32_t in_group_size, int32_t dtype,
+                               void* stream) {
+  aqlm_b200_weight_t w = make_weight(codes, codebooks, scales, nullptr, in_features, out_features, 1, 16, in_group_size, dtype);
+  return aqlm_b200_dequant(&w, weight_out, 1, stream);
+}
+int aqlm_b200_code2x8_dequant(const void* codes, const void* codebooks, const void* scales, void* weight_out,
+                              int64_t in_features, int64_t out_features, int32_t dtype, void* stream) {
+  aqlm_b200_weight_t w = make_weight(codes, codebooks, scales, nullptr, in_features, out_features, 2, 8, 8, dtype);
+  return aqlm_b200_dequant(&w, weight_out, 1, stream);
+}
+int aqlm_b200_code1x8_dequant(const void* codes, const void* codebooks, const void* scales, void* weight_out,
+                              int64_t in_features, int64_t out_features, int32_t dtype, void* stream) {
+  aqlm_b200_weight_t w = make_weight(codes, codebooks, scales, nullptr, in_features, out_features, 1, 8, 8, dtype);
+  return aqlm_b200_dequant(&w, weight_out, 1, stream);
+}
+
+}  // extern "C"

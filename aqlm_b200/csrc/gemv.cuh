@@ -1,0 +1,229 @@
+// Fused code-gather + additive dequant + GEMV (batch <= 8 rows per pass) with scale/bias epilogue.
+//
+// Replaces Code1x16MatVec / Code2x8MatVec / CodeKx8MatVec (reference cuda_kernel.cu:7-95, 144-233,
+// 296-390) plus the host loop and the 3-4 epilogue launches around them (cuda_kernel.cpp:148-182,
+// 95-111), and the Triton path used for 8x8 (kernel_selector.py:91-94).  Not a port: the kernel is
+// persistent (grid sized from the SM count), stages x once per CTA in XOR-swizzled shared memory, reads
+// each lane's 16-byte code chunk with ONE 128-bit streaming load (the reference compiles to 8 two-byte
+// loads), accumulates in fp32, handles up to 8 batch rows per pass against one gather of the
+// weights, and applies scale+bias in the same launch.
+#pragma once
+
+#include "common.cuh"
+
+namespace aqlm_b200 {
+
+struct GemvParams {
+  const void* codes;
+  const void* codebooks;
+  const void* scales;
+  const void* bias;
+  const void* x;  // [batch, in_features]
+  void* y;        // [batch, out_features] T, or float when partial
+  int out_features;
+  int in_groups;
+  int in_features;
+  int nbits;
+  int num_codebooks;  // runtime K for the generic kernel
+  int batch;          // rows in this pass (<= BT)
+  int partial_f32;
+};
+
+constexpr int kGemvThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------
+// Vector path: a row of codes is a whole number of 16-byte chunks and K*CODE_BYTES divides 16.
+//   T          __half | __nv_bfloat16
+//   K          codebooks per group;  CODE_BYTES 1|2;  G in_group_size (8|16);  BT batch rows per pass
+//   CBS        codebooks staged in shared memory (256-entry codebooks) vs gathered from global/L2 (1x16)
+//   GM         gather flavour for the global path (see ld_gather_v4)
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int K, int CODE_BYTES, int G, int BT, bool CBS, int GM>
+__global__ void __launch_bounds__(kGemvThreads) gemv_vec_kernel(const GemvParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int GPC = 16 / (K * CODE_BYTES);  // groups per 16-byte chunk
+  constexpr int UPG = G / 8;                  // 16-byte units per group
+  const int upr = p.in_features >> 3;         // 16-byte units per x row
+
+  uint4* sx = reinterpret_cast<uint4*>(smem_raw);
+  uint4* scb = sx + BT * upr;  // [K][2^nbits][UPG] when CBS
+
+  const int tid = threadIdx.x;
+  // ---- stage x (swizzled) and, for 256-entry schemes, the codebooks -------------------------------
+  {
+    const uint4* gx = reinterpret_cast<const uint4*>(p.x);
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      if (b < p.batch) {
+        for (int u = tid; u < upr; u += kGemvThreads) sx[b * upr + swz16(u)] = gx[(size_t)b * upr + u];
+      } else {
+        for (int u = tid; u < upr; u += kGemvThreads) sx[b * upr + u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    if constexpr (CBS) {
+      const int n = (K << p.nbits) * UPG;
+      const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
+      for (int u = tid; u < n; u += kGemvThreads) scb[u] = gcb[u];
+    }
+  }
+  __syncthreads();
+
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  constexpr int kWarps = kGemvThreads / 32;
+  const int chunks = p.in_groups / GPC;
+  const size_t row_bytes = (size_t)p.in_groups * K * CODE_BYTES;
+  const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
+
+  for (int row = blockIdx.x * kWarps + warp; row < p.out_features; row += gridDim.x * kWarps) {
+    float acc[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+    const uint4* crow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.codes) + row * row_bytes);
+
+    for (int c = lane; c < chunks; c += 32) {
+      const uint4 cw = ld_stream_v4(crow + c);
+      if constexpr (K == 1) {
+        // single codebook: keep the gathered vectors packed, issue all GPC gathers before any math
+        uint4 wv[GPC][UPG];
+#pragma unroll
+        for (int e = 0; e < GPC; ++e) {
+          const uint32_t code = chunk_code<CODE_BYTES>(cw, e);
+#pragma unroll
+          for (int h = 0; h < UPG; ++h) {
+            if constexpr (CBS) wv[e][h] = scb[code * UPG + h];
+            else wv[e][h] = ld_gather_v4<GM>(gcb + (size_t)code * UPG + h);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < GPC; ++e) {
+          const int u0 = (c * GPC + e) * UPG;
+#pragma unroll
+          for (int h = 0; h < UPG; ++h) {
+#pragma unroll
+            for (int b = 0; b < BT; ++b) acc[b] = dot8<T>(wv[e][h], sx[b * upr + swz16(u0 + h)], acc[b]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < GPC; ++e) {
+          float wf[UPG][8];
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const uint32_t code = chunk_code<CODE_BYTES>(cw, e * K + k);
+            const size_t off = (((size_t)k << p.nbits) + code) * UPG;
+#pragma unroll
+            for (int h = 0; h < UPG; ++h) {
+              uint4 v;
+              if constexpr (CBS) v = scb[off + h];
+              else v = ld_gather_v4<GM>(gcb + off + h);
+              if (k == 0) unpack8<T>(v, wf[h]);
+              else accum8<T>(v, wf[h]);
+            }
+          }
+          const int u0 = (c * GPC + e) * UPG;
+#pragma unroll
+          for (int h = 0; h < UPG; ++h) {
+#pragma unroll
+            for (int b = 0; b < BT; ++b) acc[b] = dot8f<T>(wf[h], sx[b * upr + swz16(u0 + h)], acc[b]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = warp_sum(acc[b]);
+    if (lane == 0) {
+      if (p.partial_f32) {
+        float* y = reinterpret_cast<float*>(p.y);
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+          if (b < p.batch) y[(size_t)b * p.out_features + row] = acc[b];
+      } else {
+        const float s = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+        const float bv = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
+        T* y = reinterpret_cast<T*>(p.y);
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+          if (b < p.batch) y[(size_t)b * p.out_features + row] = DT<T>::from_float(fmaf(acc[b], s, bv));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Generic path: any K <= 16, any nbits <= 16, ragged rows (row bytes not a multiple of 16).  One group
+// per lane per step, scalar code loads, x read through L1.  Slow but complete (the reference falls
+// back to Triton / embedding_bag here, kernel_selector.py:91-102).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int CODE_BYTES, int G, int BT>
+__global__ void __launch_bounds__(kGemvThreads) gemv_generic_kernel(const GemvParams p) {
+  constexpr int UPG = G / 8;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int kWarps = kGemvThreads / 32;
+  const int K = p.num_codebooks;
+  const int upr = p.in_features >> 3;
+  const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
+  const uint4* gx = reinterpret_cast<const uint4*>(p.x);
+  const uint32_t mask = (1u << p.nbits) - 1u;
+
+  for (int row = blockIdx.x * kWarps + warp; row < p.out_features; row += gridDim.x * kWarps) {
+    float acc[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+    for (int j = lane; j < p.in_groups; j += 32) {
+      float wf[UPG][8];
+      const size_t cbase = ((size_t)row * p.in_groups + j) * K;
+      for (int k = 0; k < K; ++k) {
+        uint32_t code;
+        if constexpr (CODE_BYTES == 2) code = reinterpret_cast<const uint16_t*>(p.codes)[cbase + k];
+        else code = reinterpret_cast<const uint8_t*>(p.codes)[cbase + k];
+        code &= mask;
+        const size_t off = (((size_t)k << p.nbits) + code) * UPG;
+#pragma unroll
+        for (int h = 0; h < UPG; ++h) {
+          const uint4 v = ld_gather_v4<0>(gcb + off + h);
+          if (k == 0) unpack8<T>(v, wf[h]);
+          else accum8<T>(v, wf[h]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < UPG; ++h) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+          if (b < p.batch) acc[b] = dot8f<T>(wf[h], gx[(size_t)b * upr + j * UPG + h], acc[b]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = warp_sum(acc[b]);
+    if (lane == 0) {
+      if (p.partial_f32) {
+        float* y = reinterpret_cast<float*>(p.y);
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+          if (b < p.batch) y[(size_t)b * p.out_features + row] = acc[b];
+      } else {
+        const float s = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+        const float bv = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
+        T* y = reinterpret_cast<T*>(p.y);
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+          if (b < p.batch) y[(size_t)b * p.out_features + row] = DT<T>::from_float(fmaf(acc[b], s, bv));
+      }
+    }
+  }
+}
+
+// Epilogue of the sharded path (after the all-reduce of fp32 partials).
+template <typename T>
+__global__ void scale_bias_kernel(const float* __restrict__ partial, const T* __restrict__ scales,
+                                  const T* __restrict__ bias, T* __restrict__ out, int64_t batch, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * n) return;
+  const int64_t o = i % n;
+  const float s = DT<T>::to_float(scales[o]);
+  const float b = bias ? DT<T>::to_float(bias[o]) : 0.f;
+  out[i] = DT<T>::from_float(fmaf(partial[i], s, b));
+}
+
+}  // namespace aqlm_b200

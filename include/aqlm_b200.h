@@ -1,0 +1,138 @@
+/*
+ * aqlm_b200 -- C-ABI of the B200-native (sm_100a) AQLM quantized-linear hot path.
+ *
+ * This header is the drop-in boundary.  Every entry point takes plain device (or,
+ * for *_host, pinned host) pointers, sizes and a CUstream/cudaStream_t passed as `void*`; no torch types.
+ * Each function returns an aqlm_b200_status; on failure aqlm_b200_last_error() returns a message for
+ * the calling thread.  Kernels never allocate or free: the caller owns every buffer, and nothing is
+ * kept between calls (reference ownership model, cuda_kernel.cpp:159-163).  All launches go to the
+ * stream given and are CUDA-graph capturable.
+ *
+ * Reference citations are relative to /root/reference/inference_lib/src/aqlm/inference_kernels/.
+ *
+ * Tensor layouts (identical to the reference module, inference.py:39-61):
+ *   codes      [out_features, in_groups, num_codebooks]   int8 (nbits<=8) | int16 (nbits<=16), two's-complement
+ *              storage of UNSIGNED codes (utils.py:23-31) -- kernels reinterpret, never sign-extend
+ *   codebooks  [num_codebooks, 2^nbits, 1, in_group_size]  f16 | bf16
+ *   scales     [out_features] (the module's [out,1,1,1])  f16 | bf16
+ *   bias       [out_features] or NULL                      f16 | bf16
+ *   input      [batch, in_features] row-major              f16 | bf16
+ *   output     [batch, out_features] row-major             f16 | bf16 (or f32 partials, see flags)
+ */
+#ifndef AQLM_B200_H_
+#define AQLM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AQLM_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  AQLM_B200_OK = 0,
+  AQLM_B200_ERR_DTYPE = 1,       /* not f16/bf16 -> NotImplementedError (cuda_kernel.cpp:9-25) */
+  AQLM_B200_ERR_UNSUPPORTED = 2, /* scheme/group size not implemented -> NotImplementedError (cuda_kernel.cpp:137-144) */
+  AQLM_B200_ERR_SHAPE = 3,       /* inconsistent sizes / misaligned pointers -> ValueError */
+  AQLM_B200_ERR_CUDA = 4,        /* CUDA runtime error (the reference never checks; we do) -> RuntimeError */
+  AQLM_B200_ERR_ARCH = 5         /* device is not sm_100 -> RuntimeError */
+} aqlm_b200_status;
+
+typedef enum { AQLM_B200_F16 = 0, AQLM_B200_BF16 = 1 } aqlm_b200_dtype;
+
+/* flags for aqlm_b200_matmat_ex */
+#define AQLM_B200_FLAG_PARTIAL_F32 1u /* write UNSCALED fp32 partial sums (no scale, no bias): the per-rank
+                                          result of an in_features-sharded matvec, to be all-reduced */
+
+/* One quantized weight matrix (all pointers are device pointers). */
+typedef struct {
+  const void* codes;
+  const void* codebooks;
+  const void* scales; /* may be NULL only with AQLM_B200_FLAG_PARTIAL_F32 */
+  const void* bias;   /* NULL = no bias (Llama) */
+  int64_t in_features;
+  int64_t out_features;
+  int32_t num_codebooks;
+  int32_t nbits_per_codebook;
+  int32_t in_group_size;  /* 8 or 16 */
+  int32_t out_group_size; /* must be 1 (every reference CUDA kernel assumes it) */
+  int32_t dtype;          /* aqlm_b200_dtype of codebooks/scales/bias/input/output */
+  int32_t reserved;
+} aqlm_b200_weight_t;
+
+int aqlm_b200_version(void);
+const char* aqlm_b200_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+uint64_t aqlm_b200_launch_count(void);
+
+/* ---- generic entry points -------------------------------------------------------------------- */
+
+/* Fused code-gather + additive dequant + GEMV with the scale/bias epilogue in the same launch.
+ * Replaces code1x16_matmat / code2x8_matmat / code1x8_matmat (cuda_kernel.cpp:148-182, 387-421,
+ * 552-586: a host loop of one MatVec launch per batch row + 3-4 epilogue launches) and the Triton
+ * path the reference uses for 8x8 (kernel_selector.py:91-94).  Any batch; intended for batch <= 6. */
+int aqlm_b200_matmat(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, void* stream);
+int aqlm_b200_matmat_ex(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, uint32_t flags,
+                        void* stream);
+
+/* Fused dequant + tensor-core GEMM for large batch: W never goes to HBM.  Replaces
+ * code{1x16,2x8,1x8}_matmat_dequant (cuda_kernel.cpp:249-301, 450-484, 615-649: Dequant kernel ->
+ * full W in HBM -> cuBLAS F::linear -> epilogue). */
+int aqlm_b200_matmat_dequant(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, void* stream);
+
+/* Materialise W [out_features, in_features] (x scales when apply_scales != 0).  Replaces
+ * code{1x16,2x8,1x8}_dequant (cuda_kernel.cpp:184-227, 423-448, 588-613). */
+int aqlm_b200_dequant(const aqlm_b200_weight_t* w, void* weight_out, int apply_scales, void* stream);
+
+/* grad_input[batch, in] = (grad_output * scales) @ W_unscaled.  Replaces
+ * code*_matmat_dequant_transposed (cuda_kernel.cpp:303-354, 486-519, 651-684), with the 2x8/1x8
+ * unscaled-input defect (cuda_kernel.cpp:497,518,662,683) NOT reproduced.  `workspace` must hold
+ * out_features*in_features elements of the weight dtype. */
+int aqlm_b200_matmat_dequant_transposed(const aqlm_b200_weight_t* w, const void* grad_output, void* grad_input,
+                                        int64_t batch, void* workspace, void* stream);
+
+/* Epilogue of the sharded path: output[b,o] = (T)(partial[b,o] * scales[o] + bias[o]) after the
+ * all-reduce of the fp32 partials (new work; the reference has no multi-GPU hot path). */
+int aqlm_b200_scale_bias(const float* partial, const void* scales, const void* bias, void* output, int64_t batch,
+                         int64_t out_features, int32_t dtype, void* stream);
+
+/* End-to-end variant with HOST buffers (pinned): H2D copy of `input_host` into `input_dev`, the fused
+ * matmat, D2H copy of the result into `output_host`, and a stream synchronize.  `input_dev`/`output_dev`
+ * are caller-owned device scratch of batch*in_features / batch*out_features elements. */
+int aqlm_b200_matmat_host(const aqlm_b200_weight_t* w, const void* input_host, void* output_host, void* input_dev,
+                          void* output_dev, int64_t batch, void* stream);
+
+/* ---- flat wrappers named after the reference's pybind functions (cuda_kernel.cpp:686-699) ------
+ * input [batch,in], codes, codebooks, scales, bias (nullable), output [batch,out]. */
+int aqlm_b200_code1x16_matmat(const void* input, const void* codes, const void* codebooks, const void* scales,
+                              const void* bias, void* output, int64_t batch, int64_t in_features,
+                              int64_t out_features, int32_t in_group_size, int32_t dtype, void* stream);
+int aqlm_b200_code2x8_matmat(const void* input, const void* codes, const void* codebooks, const void* scales,
+                             const void* bias, void* output, int64_t batch, int64_t in_features,
+                             int64_t out_features, int32_t dtype, void* stream);
+int aqlm_b200_code1x8_matmat(const void* input, const void* codes, const void* codebooks, const void* scales,
+                             const void* bias, void* output, int64_t batch, int64_t in_features,
+                             int64_t out_features, int32_t dtype, void* stream);
+int aqlm_b200_code1x16_matmat_dequant(const void* input, const void* codes, const void* codebooks,
+                                      const void* scales, const void* bias, void* output, int64_t batch,
+                                      int64_t in_features, int64_t out_features, int32_t in_group_size,
+                                      int32_t dtype, void* stream);
+int aqlm_b200_code2x8_matmat_dequant(const void* input, const void* codes, const void* codebooks,
+                                     const void* scales, const void* bias, void* output, int64_t batch,
+                                     int64_t in_features, int64_t out_features, int32_t dtype, void* stream);
+int aqlm_b200_code1x8_matmat_dequant(const void* input, const void* codes, const void* codebooks,
+                                     const void* scales, const void* bias, void* output, int64_t batch,
+                                     int64_t in_features, int64_t out_features, int32_t dtype, void* stream);
+int aqlm_b200_code1x16_dequant(const void* codes, const void* codebooks, const void* scales, void* weight_out,
+                               int64_t in_features, int64_t out_features, int32_t in_group_size, int32_t dtype,
+                               void* stream);
+int aqlm_b200_code2x8_dequant(const void* codes, const void* codebooks, const void* scales, void* weight_out,
+                              int64_t in_features, int64_t out_features, int32_t dtype, void* stream);
+int aqlm_b200_code1x8_dequant(const void* codes, const void* codebooks, const void* scales, void* weight_out,
+                              int64_t in_features, int64_t out_features, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AQLM_B200_H_ */

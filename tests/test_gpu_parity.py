@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) vs the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): mean|y - y_ref| / mean|y_ref| <= 1e-3 for fp16 (the reference's own metric,
+benchmark/matmul_benchmark.py:108).  We additionally hold the fp16 path to 5e-4 and check the committed golden
+vectors produced by the reference itself.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+from conftest import case_from_meta, golden_cases
+from helpers import TOL_BF16, TOL_FP16_TIGHT, TOL_NORTH_STAR, make_module, oracle_output, to_torch
+
+from oracle import aqlm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = golden_cases()
+IDS = [c["name"] for c in CASES]
+DEV = "cuda:0"
+
+
+def test_extension_is_loaded_and_device_is_b200():
+    from aqlm_b200 import _cabi
+
+    assert _cabi.lib().aqlm_b200_version() == 100
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    with open("/proc/self/maps") as f:
+        assert "libaqlm_b200.so" in f.read()
+
+
+@pytest.mark.parametrize("c", CASES, ids=IDS)
+def test_module_forward_matches_golden_reference_outputs(c, golden):
+    """QuantizedLinear.forward on CUDA vs the reference's own outputs (tests/golden, generated from the reference)."""
+    data, _ = golden
+    case = case_from_meta(c)
+    layer, t = make_module(case, DEV)
+    before = aqlm_launches()
+    y = layer(t["x"]).float().cpu().numpy()
+    assert aqlm_launches() > before, "no aqlm_b200 kernel was launched"
+    ref32 = data[f"{c['name']}/y_dequantize_gemm_fp32"]
+    ref_mod = data[f"{c['name']}/y_module_cpu_fp32"]
+    assert y.shape == ref32.shape
+    assert O.relative_error(y, ref32) < TOL_FP16_TIGHT
+    assert O.relative_error(y, ref_mod) < TOL_FP16_TIGHT
+    assert O.relative_error(y, ref32) < TOL_NORTH_STAR
+    # no single output may be off by more than a few fp16 ulps of the output scale
+    assert np.max(np.abs(y - ref32)) <= 4e-3 * np.max(np.abs(ref32)) + 1e-3
+
+
+def aqlm_launches():
+    from aqlm_b200 import _cabi
+
+    return _cabi.launch_count()
+
+
+@pytest.mark.parametrize("c", CASES, ids=IDS)
+def test_gemm_op_matches_oracle(c):
+    """The large-batch op (`*_matmat_dequant`) must agree with the oracle at every batch size too."""
+    from aqlm_b200.inference_kernels import get_forward_pass_kernel
+
+    case = case_from_meta(c)
+    t = to_torch(case, DEV)
+    op = get_forward_pass_kernel(t["codebooks"], True)
+    y = op(t["x"], t["codes"], t["codebooks"], t["scales"], t["bias"]).float().cpu().numpy()
+    assert O.relative_error(y, oracle_output(case)) < TOL_FP16_TIGHT
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if c["in_features"] <= 1100], ids=lambda c: c["name"])
+def test_dequant_matches_oracle_weight(c):
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    case = case_from_meta(c)
+    t = to_torch(case, DEV)
+    W = cuda_kernel.dequant(t["codes"], t["codebooks"], t["scales"]).float().cpu().numpy()
+    Wref = O.dequantize_weight(O.unpack_int_data(case["codes"], c["nbits"]), case["codebooks"], case["scales"])
+    assert W.shape == Wref.shape
+    # one rounding of an fp32 value to fp16: relative error <= 2^-11
+    np.testing.assert_allclose(W, Wref, rtol=2.0**-10, atol=1e-6)
+    Wu = cuda_kernel.dequant(t["codes"], t["codebooks"], None).float().cpu().numpy()
+    Wuref = O.dequantize_weight(O.unpack_int_data(case["codes"], c["nbits"]), case["codebooks"], None)
+    np.testing.assert_allclose(Wu, Wuref, rtol=2.0**-10, atol=1e-6)
+    if c["num_codebooks"] == 1:  # a single codebook vector is copied, not recomputed: bit-exact
+        np.testing.assert_array_equal(Wu, Wuref)
+
+
+SCHEMES = [(1, 16, 8), (1, 16, 16), (2, 8, 8), (1, 8, 8), (8, 8, 8), (4, 8, 8), (2, 12, 8), (3, 8, 8)]
+
+
+@pytest.mark.parametrize("K,nbits,g", SCHEMES)
+@pytest.mark.parametrize("batch", [1, 2, 3, 6, 8, 11])
+def test_all_schemes_and_batches(K, nbits, g, batch):
+    case = O.make_case(7000 + K * 100 + nbits + batch, 1024, 200, K, nbits, g, batch, bias=(batch % 2 == 0))
+    layer, t = make_module(case, DEV)
+    y = layer(t["x"]).float().cpu().numpy()
+    assert O.relative_error(y, oracle_output(case)) < TOL_FP16_TIGHT
+
+
+@pytest.mark.parametrize("K,nbits,g", [(1, 16, 8), (2, 8, 8), (8, 8, 8)])
+def test_bf16_against_bf16_fed_oracle(K, nbits, g):
+    case = O.make_case(7100 + K, 2048, 256, K, nbits, g, 2, bias=True)
+    layer, t = make_module(case, DEV, torch.bfloat16)
+    y = layer(t["x"]).float().cpu().numpy()
+    assert O.relative_error(y, oracle_output(case, torch.bfloat16)) < TOL_BF16
+
+
+@pytest.mark.parametrize("fin,fout", [(8, 1), (8, 7), (64, 3), (136, 33), (4096, 5), (14336, 16), (1032, 40)])
+def test_edge_shapes_1x16(fin, fout):
+    """Tiny, ragged (row bytes not a multiple of 16) and long-row shapes."""
+    case = O.make_case(7200 + fin + fout, fin, fout, 1, 16, 8, 1, False)
+    layer, t = make_module(case, DEV)
+    y = layer(t["x"]).float().cpu().numpy()
+    assert O.relative_error(y, oracle_output(case)) < TOL_FP16_TIGHT
+
+
+def test_leading_dims_and_noncontiguous_input():
+    case = O.make_case(7300, 512, 64, 2, 8, 8, 6, True)
+    layer, t = make_module(case, DEV)
+    ref = oracle_output(case)
+    y = layer(t["x"].reshape(2, 3, 512))
+    assert y.shape == (2, 3, 64)
+    assert O.relative_error(y.reshape(6, 64).float().cpu().numpy(), ref) < TOL_FP16_TIGHT
+    xt = t["x"].t().contiguous().t()  # same values, non-contiguous strides
+    assert not xt.is_contiguous()
+    assert O.relative_error(layer(xt).float().cpu().numpy(), ref) < TOL_FP16_TIGHT
+
+
+def test_empty_batch():
+    case = O.make_case(7301, 256, 32, 1, 16, 8, 1, False)
+    layer, t = make_module(case, DEV)
+    y = layer(t["x"][:0])
+    assert y.shape == (0, 32)
+
+
+def test_signed_storage_codes_are_not_sign_extended():
+    """Codes >= 2^(nbits-1) are stored negative (utils.py:23-26); all-0xFFFF must index the LAST codebook entry."""
+    case = O.make_case(7302, 256, 16, 1, 16, 8, 1, False)
+    case["codes"][:] = -1  # unsigned 65535
+    layer, t = make_module(case, DEV)
+    y = layer(t["x"]).float().cpu().numpy()
+    assert O.relative_error(y, oracle_output(case)) < TOL_FP16_TIGHT
+    case8 = O.make_case(7303, 256, 16, 2, 8, 8, 1, False)
+    case8["codes"][:] = -128  # unsigned 128
+    layer8, t8 = make_module(case8, DEV)
+    assert O.relative_error(layer8(t8["x"]).float().cpu().numpy(), oracle_output(case8)) < TOL_FP16_TIGHT
+
+
+def test_linearity_and_zero_input_at_full_size():
+    """Size-independent properties at BASELINE configs[1] size (4096 -> 14336, 1x16): f(0)=bias-free 0,
+    f(a*x1 + x2) = a*f(x1) + f(x2) up to fp16 rounding."""
+    fin, fout = 4096, 14336
+    g = torch.Generator(device=DEV).manual_seed(1)
+    codes = torch.randint(-32768, 32768, (fout, fin // 8, 1), dtype=torch.int16, device=DEV, generator=g)
+    codebooks = torch.randn((1, 65536, 1, 8), dtype=torch.float16, device=DEV, generator=g)
+    scales = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=DEV, generator=g)).half()
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    x1 = torch.randn((1, fin), dtype=torch.float16, device=DEV, generator=g)
+    x2 = torch.randn((1, fin), dtype=torch.float16, device=DEV, generator=g)
+    f = lambda x: cuda_kernel.matmat(x, codes, codebooks, scales, None).float()  # noqa: E731
+    assert torch.count_nonzero(f(torch.zeros_like(x1))) == 0
+    lhs = f((2.0 * x1 + x2))
+    rhs = 2.0 * f(x1) + f(x2)
+    rel = (lhs - rhs).abs().mean() / rhs.abs().mean()
+    assert rel < 2e-3
+    # batched rows equal the row-by-row results exactly (same kernel arithmetic per row)
+    xb = torch.cat([x1, x2, x1 - x2], 0)
+    yb = cuda_kernel.matmat(xb, codes, codebooks, scales, None)
+    for i in range(3):
+        assert torch.equal(yb[i], cuda_kernel.matmat(xb[i : i + 1], codes, codebooks, scales, None)[0])
+    # gemv against dequant + dense matmul on the GPU (fp32) at full size
+    W = cuda_kernel.dequant(codes, codebooks, scales).float()
+    ref = x1.float() @ W.t()
+    rel = (f(x1) - ref).abs().mean() / ref.abs().mean()
+    assert rel < TOL_FP16_TIGHT
+
+
+def test_full_size_config0_matches_oracle_c_port():
+    """BASELINE configs[0]: 4096->4096 1x16 bs=1 against the C oracle on the same inputs."""
+    from oracle import c_oracle
+
+    case = O.make_case(1000, 4096, 4096, 1, 16, 8, 1, False)
+    layer, t = make_module(case, DEV)
+    y = layer(t["x"]).float().cpu().numpy()
+    ref = c_oracle.dequantize_gemm(case["x"], case["codes"], case["codebooks"], case["scales"], None)
+    assert O.relative_error(y, ref) < TOL_FP16_TIGHT
+
+
+def test_flat_c_abi_wrappers():
+    """Call the flat entry points (named after the reference pybind functions) directly through ctypes."""
+    from aqlm_b200 import _cabi
+
+    L = _cabi.lib()
+    for K, nbits, entry in [(1, 16, "code1x16"), (2, 8, "code2x8"), (1, 8, "code1x8")]:
+        case = O.make_case(7400 + K + nbits, 512, 96, K, nbits, 8, 2, True)
+        t = to_torch(case, DEV)
+        y = torch.empty((2, 96), dtype=torch.float16, device=DEV)
+        st = torch.cuda.current_stream().cuda_stream
+        args = [t["x"].data_ptr(), t["codes"].data_ptr(), t["codebooks"].data_ptr(), t["scales"].data_ptr(),
+                t["bias"].data_ptr(), y.data_ptr(), 2, 512, 96]
+        for suffix in ("_matmat", "_matmat_dequant"):
+            fn = getattr(L, f"aqlm_b200_{entry}{suffix}")
+            rc = fn(*args, 8, _cabi.F16, st) if entry == "code1x16" else fn(*args, _cabi.F16, st)
+            _cabi.check(rc)
+            assert O.relative_error(y.float().cpu().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
+        W = torch.empty((96, 512), dtype=torch.float16, device=DEV)
+        fn = getattr(L, f"aqlm_b200_{entry}_dequant")
+        dargs = [t["codes"].data_ptr(), t["codebooks"].data_ptr(), t["scales"].data_ptr(), W.data_ptr(), 512, 96]
+        rc = fn(*dargs, 8, _cabi.F16, st) if entry == "code1x16" else fn(*dargs, _cabi.F16, st)
+        _cabi.check(rc)
+        Wref = O.dequantize_weight(O.unpack_int_data(case["codes"], nbits), case["codebooks"], case["scales"])
+        np.testing.assert_allclose(W.float().cpu().numpy(), Wref, rtol=2.0**-10, atol=1e-6)
+
+
+def test_host_buffer_entry_point():
+    from aqlm_b200 import _cabi
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    case = O.make_case(7500, 1024, 128, 1, 16, 8, 1, False)
+    t = to_torch(case, DEV)
+    w = cuda_kernel.make_weight(t["codes"], t["codebooks"], t["scales"].reshape(-1), None)
+    xh = torch.from_numpy(case["x"]).pin_memory()
+    yh = torch.empty((1, 128), dtype=torch.float16).pin_memory()
+    xd, yd = torch.empty_like(t["x"]), torch.empty((1, 128), dtype=torch.float16, device=DEV)
+    _cabi.check(_cabi.lib().aqlm_b200_matmat_host(ctypes.byref(w), xh.data_ptr(), yh.data_ptr(), xd.data_ptr(),
+                                                  yd.data_ptr(), 1, torch.cuda.current_stream().cuda_stream))
+    assert O.relative_error(yh.float().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
+
+
+def test_partial_f32_plus_epilogue_equals_fused():
+    """The sharded path's building blocks: sum of per-shard fp32 partials + scale_bias == fused result."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    case = O.make_case(7600, 2048, 192, 1, 16, 8, 3, True)
+    t = to_torch(case, DEV)
+    full = cuda_kernel.matmat(t["x"], t["codes"], t["codebooks"], t["scales"], t["bias"])
+    parts = 0
+    for r in range(4):
+        cs = t["codes"][:, r * 64 : (r + 1) * 64].contiguous()
+        xs = t["x"][:, r * 512 : (r + 1) * 512].contiguous()
+        parts = parts + cuda_kernel.matmat_partial(xs, cs, t["codebooks"])
+    y = cuda_kernel.scale_bias(parts, t["scales"], t["bias"], torch.float16)
+    assert O.relative_error(y.float().cpu().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
+    assert (y.float() - full.float()).abs().max() <= 2e-3 * full.float().abs().max()
+
+
+def test_error_behaviour_matches_reference():
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    case = O.make_case(7700, 256, 32, 1, 16, 8, 1, False)
+    t = to_torch(case, DEV)
+    with pytest.raises(NotImplementedError, match="only support float16 and bfloat16"):
+        cuda_kernel.matmat(t["x"].float(), t["codes"], t["codebooks"].float(), t["scales"].float(), None)
+    with pytest.raises(ValueError):
+        cuda_kernel.matmat(t["x"][:, :128], t["codes"], t["codebooks"], t["scales"], None)
+    with pytest.raises(NotImplementedError):
+        cuda_kernel.matmat(t["x"].cpu(), t["codes"].cpu(), t["codebooks"].cpu(), t["scales"].cpu(), None)
+
+
+def test_backward_wrt_input():
+    case = O.make_case(7800, 512, 96, 2, 8, 8, 9, False)
+    layer, t = make_module(case, DEV)
+    x = t["x"].clone().requires_grad_(True)
+    y = layer(x)
+    go = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, go)
+    W = O.dequantize_weight(O.unpack_int_data(case["codes"], 8), case["codebooks"], case["scales"])
+    ref = go.float().cpu().numpy() @ W
+    assert O.relative_error(gx.float().cpu().numpy(), ref) < 2e-3
+
+
+def test_cuda_graph_capture_and_replay():
+    case = O.make_case(7900, 1024, 256, 1, 16, 8, 1, False)
+    layer, t = make_module(case, DEV)
+    x = t["x"].clone()
+    layer(x)  # bind ops outside capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y = layer(x)
+    x.copy_(t["x"] * 0.5)
+    g.replay()
+    torch.cuda.synchronize()
+    ref = 0.5 * oracle_output(case)
+    assert O.relative_error(y.float().cpu().numpy(), ref) < 1e-3
