@@ -235,9 +235,9 @@ int aqlm_b200_matmat_ex(const aqlm_b200_weight_t* w, const void* input, void* ou
   const bool partial = (flags & AQLM_B200_FLAG_PARTIAL_F32) != 0;
   int rc = validate(w, !partial);
   if (rc) return rc;
-  if (!input || !output) return fail(AQLM_B200_ERR_SHAPE, "input/output pointer is NULL");
   if (batch < 0) return fail(AQLM_B200_ERR_SHAPE, "negative batch");
   if (batch == 0) return AQLM_B200_OK;
+  if (!input || !output) return fail(AQLM_B200_ERR_SHAPE, "input/output pointer is NULL");
   const DeviceInfo* di = device_info();
   if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- AQLM quantized-linear hot path on B200: matvec GB/s (code bytes) & tok/s vs the HBM roofline.
+
+Contract:
+  python bench.py --gpus N --steps K --warmup W        one JSON line on stdout (rank 0)
+  python bench.py --impl reference ...                 the reference's CPU path (oracle port) on host cores
+
+A "step" is ONE decode-token pass over every quantized linear of the model named in `config.workload`
+(q,k,v,o,gate,up,down x n_layers; batch 1; linears only), each linear with its own codes/codebooks/scales so a step
+streams the whole model's codes from HBM (1.6 GiB for Llama-3-8B >> 126 MB L2: inputs larger than L2, no flush needed).
+  N == 1 : workload = BASELINE.json configs[1], Llama-3-8B 1x16 g8 (override with --workload/--scheme)
+  N  > 1 : workload = BASELINE.json configs[4], Llama-3-70B 1x16, every linear sharded along in_features across the N
+           ranks, fp32 partials, ONE NCCL all-reduce per linear, scale+bias after the reduce ("strong" scaling).
+`value`   = code bytes of the whole model / step time, inputs resident in HBM, step replayed as one CUDA graph.
+`e2e`     = same metric through the public module API with the activations coming from pinned HOST memory every
+            step (H2D) and the last linear's output read back (D2H), both inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+MODELS = {
+    # hidden, intermediate, kv_dim, layers
+    "llama3-8b": dict(hidden=4096, inter=14336, kv=1024, layers=32),
+    "llama3-70b": dict(hidden=8192, inter=28672, kv=1024, layers=80),
+    "llama2-7b": dict(hidden=4096, inter=11008, kv=4096, layers=32),
+}
+
+
+def layer_linears(model: str):
+    m = MODELS[model]
+    h, i, kv = m["hidden"], m["inter"], m["kv"]
+    return [("q_proj", h, h), ("k_proj", h, kv), ("v_proj", h, kv), ("o_proj", h, h), ("gate_proj", h, i),
+            ("up_proj", h, i), ("down_proj", i, h)]
+
+
+def code_bytes(fin, fout, K, nbits, g=8):
+    return fout * (fin // g) * K * ((nbits + 7) // 8)
+
+
+def model_code_bytes(model, K, nbits, n_layers):
+    return n_layers * sum(code_bytes(fin, fout, K, nbits) for _, fin, fout in layer_linears(model))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU side: the reference's CPU path (oracle C port), used for cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------------------
+def cpu_layer_sample(model, K, nbits, target_seconds, nthreads=0):
+    """Time the oracle's C port of `dequantize_gemm` (reference inference_kernels/dequantization.py:9-21 -- the path
+    QuantizedLinear.forward takes on CPU for 1x16, kernel_selector.py:99-102) or, for 256-entry codebooks, of the Numba
+    LUT kernel (numba_kernel.py:37-48, kernel_selector.py:95-98) on ONE decoder layer's 7 linears, bs=1, fp32."""
+    import numpy as np
+
+    from oracle import c_oracle
+
+    c_oracle.build()
+    threads = nthreads or c_oracle.num_threads()
+    rng = np.random.default_rng(0)
+    lins = []
+    for _, fin, fout in layer_linears(model):
+        codes = rng.integers(-(2 ** (nbits - 1)), 2 ** (nbits - 1), size=(fout, fin // 8, K)).astype(
+            np.int8 if nbits <= 8 else np.int16)
+        cb = rng.standard_normal((K, 2**nbits, 1, 8), dtype=np.float32)
+        sc = rng.standard_normal((fout, 1, 1, 1), dtype=np.float32)
+        x = rng.standard_normal((1, fin), dtype=np.float32)
+        if 2**nbits == 256:  # the reference permutes codes to [in_g, out, K] for its LUT kernel (inference.py:78-83)
+            alt = np.ascontiguousarray(np.transpose(codes, (1, 0, 2))).view(np.uint8)
+            lins.append(("lut", x, alt, cb, sc))
+        else:
+            lins.append(("dq", x, codes, cb, sc))
+    nbytes = sum(code_bytes(fin, fout, K, nbits) for _, fin, fout in layer_linears(model))
+
+    def one_pass():
+        for kind, x, codes, cb, sc in lins:
+            if kind == "lut":
+                c_oracle.lut_gemv(x[0], codes, cb, sc, threads)
+            else:
+                c_oracle.dequantize_gemm(x, codes, cb, sc, None, threads)
+
+    one_pass()  # warm-up
+    t0 = time.perf_counter()
+    one_pass()
+    t1 = time.perf_counter() - t0
+    reps = max(1, min(50, int(target_seconds / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_pass()
+    dt = (time.perf_counter() - t0) / reps
+    kernel = "numba_gemm_lut port (oracle/aqlm_oracle.c: aqlm_oracle_lut_gemv)" if 2**nbits == 256 else \
+        "dequantize_gemm port (oracle/aqlm_oracle.c: aqlm_oracle_dequantize_gemm)"
+    return dict(value=nbytes / dt / 1e9, unit="GB/s", cores=threads, kind="port", seconds_per_layer=dt,
+                sample=f"one decoder layer (7 linears, {nbytes / 2**20:.1f} MiB of codes) of {model} {K}x{nbits}, bs=1, fp32, "
+                       f"{reps} reps, {kernel}", tok_s=1.0 / (dt * MODELS[model]["layers"]))
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port; the Python reference cannot
+    travel to the GPU box), all host threads, bounded sample per step = one decoder layer."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, nbits = (int(v) for v in args.scheme.split("x"))
+    model = args.workload or ("llama3-8b" if args.gpus == 1 else "llama3-70b")
+    steps = max(1, args.steps)
+    budget = 150.0  # seconds for all steps
+    base = cpu_layer_sample(model, K, nbits, target_seconds=min(20.0, budget / 4))
+    per = base["seconds_per_layer"]
+    steps_run = max(1, min(steps, int(budget / max(per, 1e-6))))
+    line = {
+        "impl": "reference", "metric": "aqlm_matvec_code_GBps", "value": base["value"], "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": steps_run, "warmup": args.warmup, "ms_per_step": per * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "tok_s_linears_only": base["tok_s"],
+        "config": {"workload": f"{model} {K}x{nbits} g8 all-linear matvec sweep, bs=1",
+                   "step": "bounded sample: ONE decoder layer (7 linears) per step on host cores"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------------------
+def build_model(model, K, nbits, n_layers, device, rank, world):
+    """Random-init modules of the named architecture's linears (no checkpoints offline): per layer a list of
+    (module, in_features_local)."""
+    import torch
+
+    import aqlm_b200
+    from aqlm_b200.sharded import ShardedQuantizedLinear
+
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    lo, hi = (-128, 128) if nbits <= 8 else (-(2 ** (nbits - 1)), 2 ** (nbits - 1))
+    layers = []
+    for _ in range(n_layers):
+        mods = []
+        for _, fin, fout in layer_linears(model):
+            if world == 1:
+                m = aqlm_b200.QuantizedLinear(fin, fout, 8, 1, K, nbits, bias=False, device=device, dtype=torch.float16)
+                local_groups = fin // 8
+            else:
+                m = ShardedQuantizedLinear(fin, fout, 8, 1, K, nbits, bias=False, rank=rank, world_size=world,
+                                           device=device, dtype=torch.float16)
+                local_groups = fin // 8 // world
+            m.codes.data = torch.randint(lo, hi, (fout, local_groups, K), dtype=m.codes.dtype, device=device, generator=gen)
+            m.codebooks.data = torch.randn((K, 2**nbits, 1, 8), dtype=torch.float16, device=device, generator=gen)
+            m.scales.data = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=device, generator=gen)).half()
+            mods.append((m, local_groups * 8))
+        layers.append(mods)
+    return layers
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from aqlm_b200 import _cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    K, nbits = (int(v) for v in args.scheme.split("x"))
+    model = args.workload or ("llama3-8b" if world == 1 else "llama3-70b")
+    n_layers = args.layers or MODELS[model]["layers"]
+    total_bytes = model_code_bytes(model, K, nbits, n_layers)
+    peak, peak_src = measured_peaks()
+
+    layers = build_model(model, K, nbits, n_layers, device, rank, world)
+    in_sizes = sorted({n for mods in layers for _, n in mods})
+    x_dev = {n: torch.randn((1, n), dtype=torch.float16, device=device) for n in in_sizes}
+    x_host = {n: torch.randn((1, n), dtype=torch.float16).pin_memory() for n in in_sizes}
+    outs = {}
+
+    def step():
+        y = None
+        for mods in layers:
+            for m, n in mods:
+                y = m(x_dev[n])
+        outs["y"] = y
+
+    # bind kernels / NCCL outside capture, count launches of one step
+    step()
+    torch.cuda.synchronize()
+    c0 = _cabi.launch_count()
+    step()
+    torch.cuda.synchronize()
+    launches_per_step = _cabi.launch_count() - c0
+
+    graph, use_graph = None, not args.no_graph
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+        except Exception as e:  # e.g. a collective that cannot be captured on this stack
+            print(f"[bench] graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            graph, use_graph = None, False
+            torch.cuda.synchronize()
+    run = graph.replay if use_graph else step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        run()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total = timed(run, args.steps)
+    ms_step = ms_total / args.steps
+
+    # ---- e2e: pinned-host activations in, last output out, every step ---------------------------------
+    y_host = torch.empty_like(outs["y"], device="cpu").pin_memory()
+    h2d = sum(x_host[n].numel() * 2 for n in in_sizes)
+    d2h = y_host.numel() * 2
+
+    def e2e_step():
+        for n in in_sizes:
+            x_dev[n].copy_(x_host[n], non_blocking=True)
+        run()
+        y_host.copy_(outs["y"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    clocks = sampler.stop() if sampler else None
+
+    # single-GPU reference point for the SAME workload when N > 1 (rank 0, unsharded, reduced layer count if needed)
+    same_n1 = None
+    if world > 1 and rank == 0 and not args.skip_n1:
+        try:
+            l1 = build_model(model, K, nbits, min(n_layers, 16), device, 0, 1)
+            xs = {n: torch.randn((1, n), dtype=torch.float16, device=device) for n in {n for mods in l1 for _, n in mods}}
+
+            def s1():
+                for mods in l1:
+                    for m, n in mods:
+                        m(xs[n])
+            s1()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                s1()
+            for _ in range(3):
+                g1.replay()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                g1.replay()
+            b.record()
+            torch.cuda.synchronize()
+            bytes1 = model_code_bytes(model, K, nbits, min(n_layers, 16))
+            same_n1 = {"value": bytes1 / (a.elapsed_time(b) / 5 * 1e-3) / 1e9, "unit": "GB/s",
+                       "note": f"rank 0 alone, unsharded, {min(n_layers, 16)} layers of the same model"}
+            del l1, g1
+        except Exception as e:
+            same_n1 = {"error": f"{type(e).__name__}: {e}"}
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        value = total_bytes / (ms_step * 1e-3) / 1e9
+        e2e_value = total_bytes / (ms_e2e * 1e-3) / 1e9
+        n_lin = n_layers * 7
+        per_gpu_bytes = total_bytes / world
+        avg_launch_us = ms_step * 1e3 / n_lin
+        achieved = per_gpu_bytes / n_lin / (avg_launch_us * 1e-6) / 1e9
+        cpu = None
+        if world == 1 and not args.skip_cpu:
+            cpu = cpu_layer_sample(model, K, nbits, target_seconds=15.0)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(f"{model}:{K}x{nbits}:bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "aqlm_matvec_code_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "tok_s_linears_only": 1e3 / ms_step,
+            "config": {"workload": f"{model} {K}x{nbits} g8 all-linear matvec sweep, bs=1, {n_layers} layers x 7 linears",
+                       "parallelism": "single GPU" if world == 1 else f"in_features-sharded x{world}, 1 NCCL all-reduce per linear",
+                       "l2_policy": f"inputs larger than L2: {total_bytes / world / 2**20:.0f} MiB of distinct codes per GPU per step",
+                       "cuda_graph": bool(use_graph), "code_bytes_per_step": total_bytes},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "gemv (fused code-gather + dequant + dot), avg over the step's launches incl. launch gaps",
+                         "avg_launch_us": avg_launch_us, "algorithmic_bytes_per_launch": per_gpu_bytes / n_lin},
+            "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e, "tok_s_linears_only": 1e3 / ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "aqlm_b200.QuantizedLinear.forward per linear (CUDA-graph replay), pinned host in/out"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if same_n1 is not None:
+            line["same_workload_single_gpu"] = same_n1
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, *MODELS])
+    ap.add_argument("--scheme", default="1x16")
+    ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only; invalidates the number)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-n1", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
