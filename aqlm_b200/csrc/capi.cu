@@ -81,25 +81,41 @@ static int set_smem(KernelT kernel, size_t smem) {
   return AQLM_B200_OK;
 }
 
+// smem bytes of the vector GEMV: x tile + staged codebooks + per-(row,slice) partials
+static size_t vec_smem_bytes(const GemvParams& p, int K, int code_bytes, int G, int BT, bool cbs, int grid) {
+  const int gpc = 16 / (K * code_bytes);
+  const int chunks = p.in_groups / gpc;
+  const int slices = (chunks + kSliceChunks - 1) / kSliceChunks;
+  const int rows_cta = (p.out_features + grid - 1) / grid;
+  return (size_t)BT * p.in_features * 2 + (cbs ? ((size_t)K << p.nbits) * G * 2 : 0) +
+         (size_t)rows_cta * slices * BT * 4;
+}
+
 template <typename T, int K, int CB, int G, int BT, bool CBS, int GM>
 static int launch_vec(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
-  const size_t smem = (size_t)BT * p.in_features * 2 + (CBS ? ((size_t)K << p.nbits) * G * 2 : 0);
-  auto kernel = gemv_vec_kernel<T, K, CB, G, BT, CBS, GM>;
+  constexpr int THREADS = (BT <= 2) ? 1024 : 512;
+  const int grid = di->sm_count * env_int("AQLM_B200_GEMV_CTAS_PER_SM", 1);
+  const size_t smem = vec_smem_bytes(p, K, CB, G, BT, CBS, grid);
+  auto kernel = gemv_vec_kernel<T, K, CB, G, BT, CBS, GM, THREADS>;
   static std::atomic<size_t> configured{0};
   if (configured.load(std::memory_order_relaxed) < smem) {
     int rc = set_smem(kernel, smem);
     if (rc) return rc;
     configured.store(smem, std::memory_order_relaxed);
   }
-  int per_sm = (int)((size_t)di->max_smem_optin / (smem + 1024));
-  const int max_per_sm = env_int("AQLM_B200_GEMV_CTAS_PER_SM", 8);
-  if (per_sm > max_per_sm) per_sm = max_per_sm;
-  if (per_sm < 1) per_sm = 1;
-  int blocks = (p.out_features + 7) / 8;
-  if (blocks > di->sm_count * per_sm) blocks = di->sm_count * per_sm;
-  kernel<<<blocks, kGemvThreads, smem, st>>>(p);
+  // PDL launch: this kernel's weight-only prologue may overlap the previous kernel's tail (see gemv.cuh).
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = env_int("AQLM_B200_PDL", 1) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
   count_launch();
-  AQLM_CUDA_CHECK(cudaGetLastError());
   return AQLM_B200_OK;
 }
 
@@ -120,9 +136,11 @@ static int dispatch_bt(const aqlm_b200_weight_t* w, const GemvParams& p, const D
   const size_t row_bytes = (size_t)p.in_groups * K * code_bytes;
   const bool vec_ok = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(w->codes) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) && !env_int("AQLM_B200_FORCE_GENERIC", 0);
-  const size_t x_smem = (size_t)BT * p.in_features * 2;
-  const size_t budget = (size_t)di->max_smem_optin - 2048;
-  if (vec_ok && nbits == 16 && K == 1 && x_smem <= budget) {
+  const size_t budget = (size_t)di->max_smem_optin - 1024;
+  const int grid = di->sm_count * env_int("AQLM_B200_GEMV_CTAS_PER_SM", 1);
+  const bool pow2k = (K == 1 || K == 2 || K == 4 || K == 8);
+  const size_t need = pow2k ? vec_smem_bytes(p, K, code_bytes, G, BT, nbits == 8, grid) : (size_t)-1;
+  if (vec_ok && nbits == 16 && K == 1 && need <= budget) {
     const int gm = env_int("AQLM_B200_GATHER_MODE", 0);
     if (G == 8) {
       if (gm == 1) return launch_vec<T, 1, 2, 8, BT, false, 1>(p, di, st);
@@ -131,7 +149,7 @@ static int dispatch_bt(const aqlm_b200_weight_t* w, const GemvParams& p, const D
     }
     return launch_vec<T, 1, 2, 16, BT, false, 0>(p, di, st);
   }
-  if (vec_ok && nbits == 8 && G == 8 && x_smem + (size_t)K * 4096 <= budget) {
+  if (vec_ok && nbits == 8 && G == 8 && pow2k && need <= budget) {
     if (K == 1) return launch_vec<T, 1, 1, 8, BT, true, 0>(p, di, st);
     if (K == 2) return launch_vec<T, 2, 1, 8, BT, true, 0>(p, di, st);
     if (K == 4) return launch_vec<T, 4, 1, 8, BT, true, 0>(p, di, st);

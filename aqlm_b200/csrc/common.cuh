@@ -102,6 +102,11 @@ __device__ __forceinline__ uint4 ld_gather_v4(const void* p) {
   return r;
 }
 
+// Programmatic dependent launch (PDL).  Both are no-ops when the kernel was launched without the
+// programmatic-stream-serialization attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -29,7 +29,8 @@ struct GemvParams {
   int partial_f32;
 };
 
-constexpr int kGemvThreads = 256;
+constexpr int kGemvThreads = 256;  // generic (fallback) kernel
+constexpr int kSliceChunks = 32;   // one K-slice = 32 16-byte code chunks = one coalesced 512-byte warp load
 
 // ---------------------------------------------------------------------------------------------------
 // Vector path: a row of codes is a whole number of 16-byte chunks and K*CODE_BYTES divides 16.
@@ -37,52 +38,83 @@ constexpr int kGemvThreads = 256;
 //   K          codebooks per group;  CODE_BYTES 1|2;  G in_group_size (8|16);  BT batch rows per pass
 //   CBS        codebooks staged in shared memory (256-entry codebooks) vs gathered from global/L2 (1x16)
 //   GM         gather flavour for the global path (see ld_gather_v4)
+//   THREADS    CTA size; the grid is persistent: (SM count) x (CTAs per SM that fit)
+//
+// Work decomposition (load balance is what matters: the kernel is bound by the per-SM gather rate, so every
+// SM must get the same number of gathers): output rows are dealt round-robin to CTAs (row r -> CTA r % grid),
+// each row is cut into K-slices of 32 chunks, and the (row, slice) tasks of a CTA are dealt round-robin to its
+// warps.  A warp reduces its task with shuffles and parks the partial in shared memory; after one barrier the
+// CTA adds the slices of each of its rows IN A FIXED ORDER (deterministic, batch-invariant) and applies
+// scale + bias.  No atomics, no second launch.
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int K, int CODE_BYTES, int G, int BT, bool CBS, int GM>
-__global__ void __launch_bounds__(kGemvThreads) gemv_vec_kernel(const GemvParams p) {
+template <typename T, int K, int CODE_BYTES, int G, int BT, bool CBS, int GM, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) gemv_vec_kernel(const GemvParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int GPC = 16 / (K * CODE_BYTES);  // groups per 16-byte chunk
   constexpr int UPG = G / 8;                  // 16-byte units per group
+  constexpr int kWarps = THREADS / 32;
   const int upr = p.in_features >> 3;         // 16-byte units per x row
+  // PDL: let the next kernel in the stream start launching; everything below that touches only WEIGHTS
+  // (codes, codebooks) may overlap the previous kernel's tail.  x and y are touched after griddep_wait().
+  griddep_launch_dependents();
+  if ((int)blockIdx.x >= p.out_features) return;
 
   uint4* sx = reinterpret_cast<uint4*>(smem_raw);
   uint4* scb = sx + BT * upr;  // [K][2^nbits][UPG] when CBS
+  float* spart = reinterpret_cast<float*>(scb + (CBS ? (K << p.nbits) * UPG : 0));  // [rows_cta][slices][BT]
 
   const int tid = threadIdx.x;
-  // ---- stage x (swizzled) and, for 256-entry schemes, the codebooks -------------------------------
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int chunks = p.in_groups / GPC;
+  const int slices = (chunks + kSliceChunks - 1) / kSliceChunks;
+  const int rows_cta = (p.out_features - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tasks = rows_cta * slices;
+  const size_t row_bytes = (size_t)p.in_groups * K * CODE_BYTES;
+  const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
+
+  // code chunk of task t for this lane (zero chunk when the lane is past the end of the row)
+  auto load_codes = [&](int t, bool& live) -> uint4 {
+    const int ri = t / slices;
+    const int sl = t - ri * slices;
+    const int c = sl * kSliceChunks + lane;
+    live = (t < tasks) && (c < chunks);
+    if (!live) return make_uint4(0, 0, 0, 0);
+    const int row = (int)blockIdx.x + ri * (int)gridDim.x;
+    return ld_stream_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.codes) + row * row_bytes) + c);
+  };
+
+  // ---- prologue: first code chunk in flight, codebooks (weights) staged, THEN wait for x -----------
+  bool live_next = false;
+  uint4 cw_next = load_codes(warp, live_next);
+  if constexpr (CBS) {
+    const int n = (K << p.nbits) * UPG;
+    for (int u = tid; u < n; u += THREADS) scb[u] = gcb[u];
+  }
+  griddep_wait();
   {
     const uint4* gx = reinterpret_cast<const uint4*>(p.x);
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
       if (b < p.batch) {
-        for (int u = tid; u < upr; u += kGemvThreads) sx[b * upr + swz16(u)] = gx[(size_t)b * upr + u];
+        for (int u = tid; u < upr; u += THREADS) sx[b * upr + swz16(u)] = gx[(size_t)b * upr + u];
       } else {
-        for (int u = tid; u < upr; u += kGemvThreads) sx[b * upr + u] = make_uint4(0, 0, 0, 0);
+        for (int u = tid; u < upr; u += THREADS) sx[b * upr + u] = make_uint4(0, 0, 0, 0);
       }
-    }
-    if constexpr (CBS) {
-      const int n = (K << p.nbits) * UPG;
-      const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
-      for (int u = tid; u < n; u += kGemvThreads) scb[u] = gcb[u];
     }
   }
   __syncthreads();
 
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  constexpr int kWarps = kGemvThreads / 32;
-  const int chunks = p.in_groups / GPC;
-  const size_t row_bytes = (size_t)p.in_groups * K * CODE_BYTES;
-  const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
-
-  for (int row = blockIdx.x * kWarps + warp; row < p.out_features; row += gridDim.x * kWarps) {
+  for (int t = warp; t < tasks; t += kWarps) {
+    const uint4 cw = cw_next;
+    const bool live = live_next;
+    cw_next = load_codes(t + kWarps, live_next);  // prefetch: hides the HBM latency of the code stream
+    const int sl = t % slices;
+    const int c = sl * kSliceChunks + lane;
     float acc[BT];
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc[b] = 0.f;
-    const uint4* crow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.codes) + row * row_bytes);
-
-    for (int c = lane; c < chunks; c += 32) {
-      const uint4 cw = ld_stream_v4(crow + c);
+    if (live) {
       if constexpr (K == 1) {
         // single codebook: keep the gathered vectors packed, issue all GPC gathers before any math
         uint4 wv[GPC][UPG];
@@ -133,19 +165,26 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_vec_kernel(const GemvParams
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc[b] = warp_sum(acc[b]);
     if (lane == 0) {
-      if (p.partial_f32) {
-        float* y = reinterpret_cast<float*>(p.y);
 #pragma unroll
-        for (int b = 0; b < BT; ++b)
-          if (b < p.batch) y[(size_t)b * p.out_features + row] = acc[b];
-      } else {
-        const float s = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
-        const float bv = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
-        T* y = reinterpret_cast<T*>(p.y);
-#pragma unroll
-        for (int b = 0; b < BT; ++b)
-          if (b < p.batch) y[(size_t)b * p.out_features + row] = DT<T>::from_float(fmaf(acc[b], s, bv));
-      }
+      for (int b = 0; b < BT; ++b) spart[(size_t)t * BT + b] = acc[b];
+    }
+  }
+  __syncthreads();
+
+  // ---- fixed-order reduction over slices + epilogue ------------------------------------------------
+  for (int i = tid; i < rows_cta * BT; i += THREADS) {
+    const int ri = i / BT;
+    const int b = i - ri * BT;
+    if (b >= p.batch) continue;
+    const int row = (int)blockIdx.x + ri * (int)gridDim.x;
+    float v = 0.f;
+    for (int sl = 0; sl < slices; ++sl) v += spart[((size_t)ri * slices + sl) * BT + b];
+    if (p.partial_f32) {
+      reinterpret_cast<float*>(p.y)[(size_t)b * p.out_features + row] = v;
+    } else {
+      const float s = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+      const float bv = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
+      reinterpret_cast<T*>(p.y)[(size_t)b * p.out_features + row] = DT<T>::from_float(fmaf(v, s, bv));
     }
   }
 }

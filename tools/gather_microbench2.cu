@@ -151,6 +151,86 @@ __global__ void __launch_bounds__(TH) k_gather4(const uint4* __restrict__ codes,
   if (acc.x == 0x12345 && acc.y == 0x777) out[0] = acc;
 }
 
+// ---- mix_g4: per chunk, NG4 gather4 instructions (4 codes each) via TMA and the other codes via LDG -----
+template <int NG4>
+__global__ void __launch_bounds__(TH) k_mix_g4(const uint4* __restrict__ codes, size_t nchunks, const uint4* __restrict__ table,
+                                               const __grid_constant__ CUtensorMap tmap, uint4* out) {
+  extern __shared__ __align__(128) uint4 slots[];  // [TH][8] : one 128-byte slot per thread, first 64 B used
+  __shared__ __align__(8) uint64_t bar_mem;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bar_mem);
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  uint32_t parity = 0;
+  const uint32_t my = (uint32_t)__cvta_generic_to_shared(slots + threadIdx.x * 8);
+  // each thread handles 2 chunks per round: chunk A fully via LDG (8 codes), chunk B: 4*NG4 codes via gather4, rest LDG
+  for (size_t c0 = (size_t)blockIdx.x * TH * 2; c0 < nchunks; c0 += (size_t)gridDim.x * TH * 2) {
+    const size_t ca = c0 + threadIdx.x, cb = c0 + TH + threadIdx.x;
+    const bool la = ca < nchunks, lb = cb < nchunks;
+    uint4 cwa = la ? ld_stream(codes + ca) : make_uint4(0, 0, 0, 0);
+    uint4 cwb = lb ? ld_stream(codes + cb) : make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+      size_t n_live = (nchunks > c0 + TH) ? ((nchunks - c0 - TH) < (size_t)TH ? (nchunks - c0 - TH) : (size_t)TH) : 0;
+      mbar_expect_tx(bar, (uint32_t)(n_live * NG4 * 64));
+    }
+    __syncthreads();
+    if (lb) {
+#pragma unroll
+      for (int h = 0; h < NG4; ++h) {
+        const int r0 = code_of(cwb, 4 * h), r1 = code_of(cwb, 4 * h + 1), r2 = code_of(cwb, 4 * h + 2), r3 = code_of(cwb, 4 * h + 3);
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+            ::"r"(my + h * 64), "l"(&tmap), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+      }
+    }
+    uint4 v[16];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint4* pp = table + code_of(cwa, e);
+      asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[e].x), "=r"(v[e].y), "=r"(v[e].z), "=r"(v[e].w) : "l"(pp));
+    }
+#pragma unroll
+    for (int e = 4 * NG4; e < 8; ++e) {
+      const uint4* pp = table + code_of(cwb, e);
+      asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[8 + e].x), "=r"(v[8 + e].y), "=r"(v[8 + e].z), "=r"(v[8 + e].w) : "l"(pp));
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+#pragma unroll
+    for (int e = 0; e < 4 * NG4; ++e) v[8 + e] = slots[threadIdx.x * 8 + e];
+    if (la) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ACC(v[e]);
+    }
+    if (lb) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ACC(v[8 + e]);
+    }
+  }
+  if (acc.x == 0x12345 && acc.y == 0x777) out[0] = acc;
+}
+
+// ---- mix_tex: half of the codes via LDG, half via the texture unit -----------------------------------
+__global__ void __launch_bounds__(TH) k_mix_tex(const uint4* __restrict__ codes, size_t nchunks, const uint4* __restrict__ table,
+                                                cudaTextureObject_t tex, uint4* out) {
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  for (size_t c = (size_t)blockIdx.x * TH + threadIdx.x; c < nchunks; c += (size_t)gridDim.x * TH) {
+    uint4 cw = ld_stream(codes + c);
+    uint4 v[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint4* pp = table + code_of(cw, e);
+      asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[e].x), "=r"(v[e].y), "=r"(v[e].z), "=r"(v[e].w) : "l"(pp));
+    }
+#pragma unroll
+    for (int e = 4; e < 8; ++e) v[e] = tex1Dfetch<uint4>(tex, (int)code_of(cw, e));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ACC(v[e]);
+  }
+  if (acc.x == 0x12345 && acc.y == 0x777) out[0] = acc;
+}
+
 // ---- ldgsts: per-code cp.async 16 B ------------------------------------------------------------------
 __global__ void __launch_bounds__(TH) k_ldgsts(const uint4* __restrict__ codes, size_t nchunks, const uint4* __restrict__ table, uint4* out) {
   extern __shared__ __align__(128) uint4 slots[];  // [TH][8]
@@ -265,6 +345,46 @@ int main(int argc, char** argv) {
       } else {
         CK(cudaFuncSetAttribute(k_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ms = time_ms([&](int i) { k_bulk<false><<<sms * cps, TH, smem>>>(BUF(i), nchunks, table, out); }, iters);
+      }
+      CK(cudaDeviceSynchronize());
+      report(variant, cps, TH, ms, 1.0);
+    }
+  } else if (!strcmp(variant, "mix_tex")) {
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = table;
+    rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+    rd.res.linear.sizeInBytes = 65536 * sizeof(uint4);
+    cudaTextureDesc td = {};
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex;
+    CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    for (int cps : {4, 8}) {
+      float ms = time_ms([&](int i) { k_mix_tex<<<sms * cps, TH>>>(BUF(i), nchunks, table, tex, out); }, iters);
+      report(variant, cps, TH, ms, 1.0);
+    }
+  } else if (!strncmp(variant, "mix_g4", 6)) {
+    encode_fn encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres));
+    CUtensorMap tmap;
+    cuuint64_t dims[2] = {8, 65536};
+    cuuint64_t strides[1] = {16};
+    cuuint32_t box[2] = {8, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, table, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("{\"variant\": \"%s\", \"error\": \"cuTensorMapEncodeTiled=%d\"}\n", variant, (int)r); return 0; }
+    const bool two = !strcmp(variant, "mix_g4x2");
+    for (int cps : {2, 4, 6}) {
+      const size_t smem = TH * 8 * 16;
+      float ms;
+      if (two) {
+        CK(cudaFuncSetAttribute(k_mix_g4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ms = time_ms([&](int i) { k_mix_g4<2><<<sms * cps, TH, smem>>>(BUF(i), nchunks, table, tmap, out); }, iters);
+      } else {
+        CK(cudaFuncSetAttribute(k_mix_g4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ms = time_ms([&](int i) { k_mix_g4<1><<<sms * cps, TH, smem>>>(BUF(i), nchunks, table, tmap, out); }, iters);
       }
       CK(cudaDeviceSynchronize());
       report(variant, cps, TH, ms, 1.0);
