@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "dequant.cuh"
+#include "gemm_tcgen05.cuh"
 #include "gemv.cuh"
 
 namespace aqlm_b200 {
@@ -220,6 +221,138 @@ static int dequant_typed(const aqlm_b200_weight_t* w, void* out, int apply_scale
   return AQLM_B200_OK;
 }
 
+// ---- fused dequant + tcgen05 GEMM: host side ------------------------------------------------------
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn get_tmap_encode() {
+  static tmap_encode_fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tmap_encode_fn>(p);
+  });
+  return fn;
+}
+
+struct GemmPlan {
+  bool ok = false;       // tcgen05 path applicable
+  int m_tiles = 0, n_tiles = 0, n_tile = 0, ksplit = 1, stages = 0, total_kblocks = 0;
+  size_t counters_bytes = 0, partials_bytes = 0;
+};
+
+static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const DeviceInfo* di, bool allow_split) {
+  GemmPlan g;
+  const int K = w->num_codebooks, nbits = w->nbits_per_codebook;
+  const int cb = nbits <= 8 ? 1 : 2;
+  if (w->in_group_size != 8 || (nbits != 8 && nbits != 16)) return g;
+  if (!(K == 1 || K == 2 || K == 4 || K == 8) || 8 * K * cb > kCodeTileBytes) return g;
+  if (w->in_features % kGemmBlockK != 0) return g;
+  if ((reinterpret_cast<uintptr_t>(w->codes) & 15) != 0) return g;
+  if (env_int("AQLM_B200_DISABLE_TCGEN05", 0)) return g;
+  g.total_kblocks = (int)(w->in_features / kGemmBlockK);
+  g.m_tiles = (int)((w->out_features + kGemmBlockM - 1) / kGemmBlockM);
+  if (batch <= 256) {
+    g.n_tile = (int)((batch + 15) / 16 * 16);
+    g.n_tiles = 1;
+  } else {
+    g.n_tile = 256;
+    g.n_tiles = (int)((batch + 255) / 256);
+  }
+  const size_t budget = (size_t)di->max_smem_optin;
+  int S = 6;
+  while (S > 2 && gemm_smem_layout(S, g.n_tile).total > budget) --S;
+  if (gemm_smem_layout(S, g.n_tile).total > budget) return g;
+  const int forced_s = env_int("AQLM_B200_GEMM_STAGES", 0);
+  if (forced_s >= 2 && forced_s <= S) S = forced_s;
+  g.stages = S;
+  int ks = 1;
+  if (allow_split) {
+    const int tiles = g.m_tiles * g.n_tiles;
+    ks = di->sm_count / tiles;
+    const int forced = env_int("AQLM_B200_GEMM_KSPLIT", 0);
+    if (forced > 0) ks = forced;
+    if (ks > g.total_kblocks / 2) ks = g.total_kblocks / 2;
+    if (ks < 1) ks = 1;
+  }
+  g.ksplit = ks;
+  g.counters_bytes = (((size_t)g.m_tiles * g.n_tiles * 4) + 255) & ~(size_t)255;
+  g.partials_bytes = ks > 1 ? (size_t)g.m_tiles * g.n_tiles * ks * g.n_tile * kGemmBlockM * 4 : 0;
+  g.ok = true;
+  return g;
+}
+
+template <typename T, int K, int CB>
+static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, const GemmPlan& g,
+                       void* workspace, cudaStream_t st) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc) return fail(AQLM_B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  CUtensorMap tx, tc;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)w->in_features, (cuuint64_t)batch};
+    cuuint64_t strides[1] = {(cuuint64_t)w->in_features * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)g.n_tile};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tx, DT<T>::is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void*>(input), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AQLM_B200_ERR_CUDA, "cuTensorMapEncodeTiled(x) failed: %d", (int)r);
+  }
+  {
+    const size_t row_bytes = (size_t)(w->in_features / 8) * K * CB;
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)w->out_features};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)kCodeTileBytes, (cuuint32_t)kGemmBlockM};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w->codes), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AQLM_B200_ERR_CUDA, "cuTensorMapEncodeTiled(codes) failed: %d", (int)r);
+  }
+  GemmParams p;
+  p.codebooks = w->codebooks;
+  p.scales = w->scales;
+  p.bias = w->bias;
+  p.y = output;
+  p.ws_counters = g.ksplit > 1 ? reinterpret_cast<unsigned int*>(workspace) : nullptr;
+  p.ws_partials = g.ksplit > 1 ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + g.counters_bytes) : nullptr;
+  p.out_features = (int)w->out_features;
+  p.batch = (int)batch;
+  p.nbits = w->nbits_per_codebook;
+  p.total_kblocks = g.total_kblocks;
+  p.ksplit = g.ksplit;
+  p.n_tile = g.n_tile;
+  p.stages = g.stages;
+  const size_t smem = gemm_smem_layout(g.stages, g.n_tile).total;
+  auto kernel = gemm_dequant_kernel<T, K, CB>;
+  static std::atomic<size_t> configured{0};
+  if (configured.load(std::memory_order_relaxed) < smem) {
+    AQLM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured.store(smem, std::memory_order_relaxed);
+  }
+  kernel<<<dim3(g.m_tiles, g.ksplit, g.n_tiles), kGemmThreads, smem, st>>>(tx, tc, p);
+  count_launch();
+  AQLM_CUDA_CHECK(cudaGetLastError());
+  return AQLM_B200_OK;
+}
+
+template <typename T>
+static int gemm_typed(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, const GemmPlan& g,
+                      void* workspace, cudaStream_t st) {
+  const int K = w->num_codebooks, cb = w->nbits_per_codebook <= 8 ? 1 : 2;
+  if (cb == 2 && K == 1) return launch_gemm<T, 1, 2>(w, input, output, batch, g, workspace, st);
+  if (cb == 2 && K == 2) return launch_gemm<T, 2, 2>(w, input, output, batch, g, workspace, st);
+  if (cb == 2 && K == 4) return launch_gemm<T, 4, 2>(w, input, output, batch, g, workspace, st);
+  if (cb == 2 && K == 8) return launch_gemm<T, 8, 2>(w, input, output, batch, g, workspace, st);
+  if (K == 1) return launch_gemm<T, 1, 1>(w, input, output, batch, g, workspace, st);
+  if (K == 2) return launch_gemm<T, 2, 1>(w, input, output, batch, g, workspace, st);
+  if (K == 4) return launch_gemm<T, 4, 1>(w, input, output, batch, g, workspace, st);
+  return launch_gemm<T, 8, 1>(w, input, output, batch, g, workspace, st);
+}
+
 static aqlm_b200_weight_t make_weight(const void* codes, const void* codebooks, const void* scales, const void* bias,
                                       int64_t in_features, int64_t out_features, int K, int nbits, int g, int dtype) {
   aqlm_b200_weight_t w;
@@ -267,11 +400,39 @@ int aqlm_b200_matmat(const aqlm_b200_weight_t* w, const void* input, void* outpu
   return aqlm_b200_matmat_ex(w, input, output, batch, 0, stream);
 }
 
+size_t aqlm_b200_matmat_dequant_workspace_bytes(const aqlm_b200_weight_t* w, int64_t batch) {
+  if (validate(w, true) != AQLM_B200_OK || batch <= 0) return 0;
+  const DeviceInfo* di = device_info();
+  if (!di) return 0;
+  const GemmPlan g = gemm_plan(w, batch, di, true);
+  if (!g.ok || g.ksplit <= 1) return 0;
+  return g.counters_bytes + g.partials_bytes;
+}
+
+int aqlm_b200_matmat_dequant_ws(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate(w, true);
+  if (rc) return rc;
+  if (batch < 0) return fail(AQLM_B200_ERR_SHAPE, "negative batch");
+  if (batch == 0) return AQLM_B200_OK;
+  if (!input || !output) return fail(AQLM_B200_ERR_SHAPE, "input/output pointer is NULL");
+  const DeviceInfo* di = device_info();
+  if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmPlan g = gemm_plan(w, batch, di, workspace != nullptr);
+  if (g.ok && g.ksplit > 1 && workspace_bytes < g.counters_bytes + g.partials_bytes) g = gemm_plan(w, batch, di, false);
+  if (!g.ok || (reinterpret_cast<uintptr_t>(input) & 15) != 0) {
+    // shapes the tensor-core kernel does not cover (in_group 16, in_features % 64 != 0, odd KxN):
+    // batch passes of 8 rows through the fused gather+dequant+dot kernel
+    return aqlm_b200_matmat_ex(w, input, output, batch, 0, stream);
+  }
+  if (w->dtype == AQLM_B200_F16) return gemm_typed<__half>(w, input, output, batch, g, workspace, st);
+  return gemm_typed<__nv_bfloat16>(w, input, output, batch, g, workspace, st);
+}
+
 int aqlm_b200_matmat_dequant(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch,
                              void* stream) {
-  // v0: batch processed in passes of 8 rows through the fused gather+dequant+dot kernel (weights are
-  // re-gathered per pass).  To be replaced by the tcgen05 fused dequant+GEMM.
-  return aqlm_b200_matmat_ex(w, input, output, batch, 0, stream);
+  return aqlm_b200_matmat_dequant_ws(w, input, output, batch, nullptr, 0, stream);  // no workspace: no split-K
 }
 
 int aqlm_b200_dequant(const aqlm_b200_weight_t* w, void* weight_out, int apply_scales, void* stream) {

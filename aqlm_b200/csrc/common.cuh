@@ -52,6 +52,7 @@ template <typename T>
 struct DT;
 template <>
 struct DT<__half> {
+  static constexpr bool is_bf16 = false;
   static __device__ __forceinline__ float2 unpack2(uint32_t v) {
     return __half22float2(*reinterpret_cast<const __half2*>(&v));
   }
@@ -64,6 +65,7 @@ struct DT<__half> {
 };
 template <>
 struct DT<__nv_bfloat16> {
+  static constexpr bool is_bf16 = true;
   static __device__ __forceinline__ float2 unpack2(uint32_t v) {
     // bf16 -> f32 is a 16-bit shift: exact and cheaper than the cvt path
     return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));

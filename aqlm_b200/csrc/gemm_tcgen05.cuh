@@ -1,0 +1,363 @@
+// Fused additive-dequant + tensor-core GEMM for batch > 6:  Y[bs, out] = X[bs, in] . W^T, W never touches HBM.
+//
+// Replaces code{1x16,2x8,1x8}_matmat_dequant (reference cuda_kernel.cpp:249-301, 450-484, 615-649), which
+// materialise W [out,in] in HBM with a Dequant kernel (cuda_kernel.cu:98-142) and then call cuBLAS.
+//
+// B200 design (tcgen05 / TMEM / TMA, hand-written PTX):
+//   D[128 x N] (fp32, TMEM)  +=  A[128 x 64] (smem, K-major, SWIZZLE_128B)  x  B[N x 64]^T (smem, K-major, SWIZZLE_128B)
+//   A = a 128-row tile of W, produced ON CHIP: producer warps read packed codes from a TMA-staged code tile,
+//       gather the codebook vectors (L2/L1) and write them straight into the swizzled UMMA layout;
+//   B = the activation tile X[n0:n0+N, k0:k0+64], TMA-loaded (OOB rows zero-filled, so any batch works);
+//   one elected thread issues tcgen05.mma (128 x N x 16, kind::f16, fp16 or bf16 operands, fp32 accumulate),
+//   tcgen05.commit releases smem stages through mbarriers; the epilogue reads TMEM with tcgen05.ld and
+//   applies scale + bias.
+// Grid = (M tiles, K splits, N tiles).  The kernel is bound by the per-SM codebook-gather rate (see
+// profiles/), so the K dimension is split to put every SM to work; split partials go through an fp32
+// workspace and the LAST-arriving CTA of each tile reduces them in a fixed order (deterministic).
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace aqlm_b200 {
+
+constexpr int kGemmThreads = 384;        // warps 0-3: TMA / MMA / TMEM-alloc, then epilogue; warps 4-11: dequant producers
+constexpr int kGemmProducerWarps = 8;
+constexpr int kGemmBlockM = 128;
+constexpr int kGemmBlockK = 64;          // 64 halves = 128 bytes = one swizzle row
+constexpr int kCodeTileBytes = 128;      // bytes of codes per row per code tile (TMA box inner extent)
+constexpr int kCodeTileStages = 2;
+
+struct GemmParams {
+  const void* codebooks;
+  const void* scales;
+  const void* bias;
+  void* y;              // [batch, out_features]
+  float* ws_partials;   // [m_tiles][n_tiles][ksplit][N][128] fp32 (ksplit > 1)
+  unsigned int* ws_counters;  // [m_tiles * n_tiles], zero on entry
+  int out_features;
+  int batch;
+  int nbits;
+  int total_kblocks;    // in_features / 64
+  int ksplit;
+  int n_tile;           // N of the MMA (multiple of 16, <= 256)
+  int stages;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(=1)<<16 | SBO(1024 B >>4)<<32 | version 1<<46 | layout 2<<61
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// UMMA instruction descriptor, kind::f16: D=f32, A/B = f16 (0) or bf16 (1), both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t umma_idesc(int ab_format, int n) {
+  return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(kGemmBlockM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory carve-up (all offsets from a 1024-byte aligned base)
+struct GemmSmem {
+  uint32_t a, b, codes, full, empty, cfull, cempty, tfull, tmem_slot, flag;
+  size_t total;
+};
+__host__ __device__ inline GemmSmem gemm_smem_layout(int stages, int n_tile) {
+  GemmSmem L;
+  size_t off = 0;
+  L.a = (uint32_t)off; off += (size_t)stages * kGemmBlockM * 128;
+  L.b = (uint32_t)off; off += (size_t)stages * n_tile * 128;
+  off = (off + 1023) & ~(size_t)1023;
+  L.codes = (uint32_t)off; off += (size_t)kCodeTileStages * kGemmBlockM * kCodeTileBytes;
+  L.full = (uint32_t)off; off += 8 * 8;
+  L.empty = (uint32_t)off; off += 8 * 8;
+  L.cfull = (uint32_t)off; off += 8 * kCodeTileStages;
+  L.cempty = (uint32_t)off; off += 8 * kCodeTileStages;
+  L.tfull = (uint32_t)off; off += 8;
+  L.tmem_slot = (uint32_t)off; off += 4;
+  L.flag = (uint32_t)off; off += 4;
+  L.total = off + 1024;  // slack for manual 1024-byte alignment of the dynamic smem base
+  return L;
+}
+
+// K = codebooks per group, CODE_BYTES = 1|2 ; in_group_size == 8.
+// bytes of codes per row per 64-wide k-block: GB = 8 groups * K * CODE_BYTES
+template <typename T, int K, int CODE_BYTES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_codes, const GemmParams p) {
+  constexpr int GB = 8 * K * CODE_BYTES;             // code bytes per row per k-block
+  constexpr int KB_PER_CTILE = kCodeTileBytes / GB;  // k-blocks covered by one code tile
+  static_assert(KB_PER_CTILE >= 1, "scheme too wide for the code tile");
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_dyn + (base - smem_u32(smem_dyn));
+  const GemmSmem L = gemm_smem_layout(p.stages, p.n_tile);
+  const int S = p.stages;
+  const int N = p.n_tile;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, split = blockIdx.y, n_blk = blockIdx.z;
+  const int m0 = m_tile * kGemmBlockM, n0 = n_blk * N;
+  // k-block range of this split (balanced, contiguous)
+  const int kb0 = (int)(((long long)p.total_kblocks * split) / p.ksplit);
+  const int kb1 = (int)(((long long)p.total_kblocks * (split + 1)) / p.ksplit);
+  const int nkb = kb1 - kb0;
+  // code tiles: aligned to KB_PER_CTILE boundaries in absolute k-block index
+  const int ct0 = kb0 / KB_PER_CTILE;
+  const int ct1 = (kb1 + KB_PER_CTILE - 1) / KB_PER_CTILE;
+
+  auto full_bar = [&](int s) { return base + L.full + 8 * s; };
+  auto empty_bar = [&](int s) { return base + L.empty + 8 * s; };
+  auto cfull_bar = [&](int s) { return base + L.cfull + 8 * s; };
+  auto cempty_bar = [&](int s) { return base + L.cempty + 8 * s; };
+  const uint32_t tfull_bar = base + L.tfull;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L.tmem_slot);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), kGemmProducerWarps + 1);  // 8 producer warps + the TMA thread (expect_tx)
+      mbar_init(empty_bar(s), 1);                      // tcgen05.commit
+    }
+    for (int s = 0; s < kCodeTileStages; ++s) {
+      mbar_init(cfull_bar(s), 1);
+      mbar_init(cempty_bar(s), kGemmProducerWarps);
+    }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < N) tmem_cols <<= 1;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L.tmem_slot), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0 && lane == 0) {
+      // ===== TMA producer: code tiles (one per KB_PER_CTILE k-blocks) and one X tile per k-block =====
+      int ct_loaded = ct0;
+      auto load_ctile = [&](int ct) {
+        const int cs = (ct - ct0) % kCodeTileStages;
+        const int it = (ct - ct0) / kCodeTileStages;
+        if (it > 0) mbar_wait(cempty_bar(cs), (it - 1) & 1);  // every producer warp released the previous tenant
+        mbar_expect_tx(cfull_bar(cs), kGemmBlockM * kCodeTileBytes);
+        tma_load_2d(base + L.codes + cs * kGemmBlockM * kCodeTileBytes, &tmap_codes, ct * kCodeTileBytes, m0, cfull_bar(cs));
+      };
+      load_ctile(ct_loaded++);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S, it = i / S;
+        if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
+        mbar_expect_tx(full_bar(s), (uint32_t)N * 128);
+        tma_load_2d(base + L.b + s * N * 128, &tmap_x, (kb0 + i) * kGemmBlockK, n0, full_bar(s));
+        // prefetch the NEXT code tile while the producers work on the current one
+        const int ct_cur = (kb0 + i) / KB_PER_CTILE;
+        if (ct_loaded < ct1 && ct_loaded <= ct_cur + 1) load_ctile(ct_loaded++);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc(sizeof(T) == 2 && DT<T>::is_bf16 ? 1 : 0, N);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S, it = i / S;
+        mbar_wait(full_bar(s), it & 1);
+        tc_fence_after();
+        const uint32_t a_addr = base + L.a + s * kGemmBlockM * 128;
+        const uint32_t b_addr = base + L.b + s * N * 128;
+#pragma unroll
+        for (int k = 0; k < kGemmBlockK / 16; ++k) {
+          umma_f16(tmem_base, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc, (i | k) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));  // frees this smem stage when the MMAs above have read it
+      }
+      umma_commit(tfull_bar);  // accumulator complete
+    } else if (warp >= 4) {
+      // ===== dequant producers: 256 threads, thread -> (row, half of the 8 groups of a k-block) =====
+      const int pt = threadIdx.x - 128;
+      const int row = pt >> 1, gh = pt & 1;
+      const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
+      constexpr int CB4 = 4 * K * CODE_BYTES;  // code bytes of this thread's 4 groups
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb0 + i;
+        const int ct = kb / KB_PER_CTILE, st_in = kb % KB_PER_CTILE;
+        const int cs = (ct - ct0) % kCodeTileStages, cit = (ct - ct0) / kCodeTileStages;
+        mbar_wait(cfull_bar(cs), cit & 1);
+        // this thread's CB4 code bytes inside the SWIZZLE_128B code tile: logical byte offset -> physical
+        uint32_t cw[CB4 / 4 > 0 ? CB4 / 4 : 1];
+        {
+          const int lbyte = st_in * GB + gh * CB4;  // logical byte in the 128-byte row (CB4-aligned)
+          const uint8_t* crow = gbase + L.codes + cs * kGemmBlockM * kCodeTileBytes + row * 128;
+#pragma unroll
+          for (int q = 0; q < (CB4 + 15) / 16; ++q) {
+            const int lb = lbyte + q * 16;
+            const int chunk = (lb >> 4) ^ (row & 7);
+            const uint8_t* src = crow + (chunk << 4) + (lb & 15);
+            if constexpr (CB4 >= 16) {
+              const uint4 v = *reinterpret_cast<const uint4*>(src);
+              cw[q * 4 + 0] = v.x; cw[q * 4 + 1] = v.y; cw[q * 4 + 2] = v.z; cw[q * 4 + 3] = v.w;
+            } else if constexpr (CB4 == 8) {
+              const uint2 v = *reinterpret_cast<const uint2*>(src);
+              cw[0] = v.x; cw[1] = v.y;
+            } else {
+              cw[0] = *reinterpret_cast<const uint32_t*>(src);
+            }
+          }
+        }
+        // release the code tile after its last k-block (all lanes of the warp have read their bytes)
+        if (st_in == KB_PER_CTILE - 1 || i == nkb - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(cempty_bar(cs));
+        }
+        // gather + additive dequant of 4 groups (issue every gather before any use)
+        uint4 wv[4][K];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const int idx = e * K + k;  // element index among this thread's codes
+            uint32_t code;
+            if constexpr (CODE_BYTES == 2) code = (cw[idx >> 1] >> ((idx & 1) * 16)) & 0xffffu;
+            else code = (cw[idx >> 2] >> ((idx & 3) * 8)) & 0xffu;
+            wv[e][k] = ld_gather_v4<0>(gcb + (((size_t)k << p.nbits) + code));
+          }
+        }
+        const int s = i % S, it = i / S;
+        if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
+        uint8_t* arow = gbase + L.a + s * kGemmBlockM * 128 + row * 128;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint4 v = wv[e][0];
+          if constexpr (K > 1) {
+            float f[8];
+            unpack8<T>(wv[e][0], f);
+#pragma unroll
+            for (int k = 1; k < K; ++k) accum8<T>(wv[e][k], f);
+            v.x = DT<T>::pack2(f[0], f[1]); v.y = DT<T>::pack2(f[2], f[3]);
+            v.z = DT<T>::pack2(f[4], f[5]); v.w = DT<T>::pack2(f[6], f[7]);
+          }
+          const int j = gh * 4 + e;  // 16-byte chunk (= group) index inside the 128-byte K row
+          *reinterpret_cast<uint4*>(arow + ((j ^ (row & 7)) << 4)) = v;
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(s));
+      }
+    }
+  }
+
+  // ===== epilogue: warps 0-3, thread <-> TMEM lane <-> output row =====
+  if (warp < 4) {
+    __syncwarp();  // lanes 1-31 of the TMA / MMA warps wait here for their lane 0 (tcgen05.ld is warp-collective)
+    const int row_in_tile = warp * 32 + lane;
+    const int row = m0 + row_in_tile;
+    const bool row_ok = row < p.out_features;
+    float sc = 1.f, bi = 0.f;
+    if (row_ok) {
+      sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+      if (p.bias) bi = DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]);
+    }
+    if (nkb > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    T* y = reinterpret_cast<T*>(p.y);
+    const size_t tile_id = (size_t)m_tile * gridDim.z + n_blk;
+    float* my_part = p.ws_partials ? p.ws_partials + ((tile_id * p.ksplit + split) * (size_t)N) * kGemmBlockM : nullptr;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t r[32];
+      if (nkb > 0) {
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r[c] = 0u;
+      }
+      if (p.ksplit == 1) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int n = n0 + c0 + c;
+          if (row_ok && c0 + c < N && n < p.batch) y[(size_t)n * p.out_features + row] = DT<T>::from_float(fmaf(__uint_as_float(r[c]), sc, bi));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c0 + c < N) my_part[(size_t)(c0 + c) * kGemmBlockM + row_in_tile] = __uint_as_float(r[c]);
+      }
+    }
+    if (p.ksplit > 1) {
+      // last-arriving split of this tile reduces all partials in split order (deterministic) and stores y
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint32_t* flag = reinterpret_cast<uint32_t*>(gbase + L.flag);
+      if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(p.ws_counters + tile_id, 1u);
+        *flag = (old == (unsigned int)p.ksplit - 1) ? 1u : 0u;
+        if (old == (unsigned int)p.ksplit - 1) p.ws_counters[tile_id] = 0u;  // leave the counter clean for the next call
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*flag) {
+        __threadfence();
+        const float* parts = p.ws_partials + (tile_id * p.ksplit) * (size_t)N * kGemmBlockM;
+        for (int c = 0; c < N; ++c) {
+          const int n = n0 + c;
+          if (n >= p.batch) break;
+          float v = 0.f;
+          for (int sp = 0; sp < p.ksplit; ++sp) v += __ldcg(parts + ((size_t)sp * N + c) * kGemmBlockM + row_in_tile);
+          if (row_ok) y[(size_t)n * p.out_features + row] = DT<T>::from_float(fmaf(v, sc, bi));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+}  // namespace aqlm_b200

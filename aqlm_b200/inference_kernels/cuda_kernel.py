@@ -127,9 +127,42 @@ def matmat(input, codes, codebooks, scales, bias=None) -> torch.Tensor:
     return _matmat_impl("aqlm_b200_matmat", input, codes, codebooks, scales, bias)
 
 
+_WORKSPACES: dict = {}  # (device index) -> persistent zero-initialised split-K workspace (counters stay zero)
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Persistent per-device workspace for the split-K GEMM.  The kernel leaves the tile counters at zero, so the
+    buffer is zeroed only when it is (re)allocated.  One workspace per device: concurrent use from several streams
+    of the same device is not supported."""
+    ws = _WORKSPACES.get(device.index)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WORKSPACES[device.index] = ws
+    return ws
+
+
 def matmat_dequant(input, codes, codebooks, scales, bias=None) -> torch.Tensor:
-    """Fused dequant + tensor-core GEMM (+scale+bias), any scheme; for large batch."""
-    return _matmat_impl("aqlm_b200_matmat_dequant", input, codes, codebooks, scales, bias)
+    """Fused dequant + tcgen05 tensor-core GEMM (+scale+bias); for large batch (reference `*_matmat_dequant`)."""
+    device = _require_cuda(input, codes, codebooks, scales, bias)
+    _dtype_code(input)
+    if input.dtype != codebooks.dtype:
+        raise ValueError(f"input dtype {input.dtype} != codebooks dtype {codebooks.dtype}")
+    w = make_weight(codes, codebooks, scales.reshape(-1), bias)
+    if input.shape[-1] != w.in_features:
+        raise ValueError(f"input has {input.shape[-1]} features, weight expects {w.in_features}")
+    flat_input = input.reshape(-1, input.shape[-1])
+    if not flat_input.is_contiguous():
+        flat_input = flat_input.contiguous()
+    batch = flat_input.shape[0]
+    flat_output = torch.empty((batch, w.out_features), dtype=input.dtype, device=device)
+    with _on_device(device):
+        L = _cabi.lib()
+        need = L.aqlm_b200_matmat_dequant_workspace_bytes(ctypes.byref(w), batch) if batch > 0 else 0
+        ws = _workspace(device, need) if need else None
+        _cabi.check(L.aqlm_b200_matmat_dequant_ws(ctypes.byref(w), flat_input.data_ptr(), flat_output.data_ptr(), batch,
+                                                  ws.data_ptr() if ws is not None else None,
+                                                  ws.numel() if ws is not None else 0, _stream_ptr(device)))
+    return flat_output.reshape(input.shape[:-1] + (w.out_features,))
 
 
 def matmat_partial(input, codes, codebooks) -> torch.Tensor:

@@ -80,6 +80,13 @@ int aqlm_b200_matmat_ex(const aqlm_b200_weight_t* w, const void* input, void* ou
  * code{1x16,2x8,1x8}_matmat_dequant (cuda_kernel.cpp:249-301, 450-484, 615-649: Dequant kernel ->
  * full W in HBM -> cuBLAS F::linear -> epilogue). */
 int aqlm_b200_matmat_dequant(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, void* stream);
+/* Same with a caller-owned workspace, which lets the kernel split the K dimension across otherwise idle SMs
+ * (the reduction is deterministic).  The first aqlm_b200_matmat_dequant_workspace_bytes() bytes... the whole
+ * workspace must be ZERO before the first use and is left zero-initialised where it matters (tile counters),
+ * so one persistent buffer per stream can be reused without memsets. */
+size_t aqlm_b200_matmat_dequant_workspace_bytes(const aqlm_b200_weight_t* w, int64_t batch);
+int aqlm_b200_matmat_dequant_ws(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* Materialise W [out_features, in_features] (x scales when apply_scales != 0).  Replaces
  * code{1x16,2x8,1x8}_dequant (cuda_kernel.cpp:184-227, 423-448, 588-613). */

@@ -284,3 +284,78 @@ def test_cuda_graph_capture_and_replay():
     torch.cuda.synchronize()
     ref = 0.5 * oracle_output(case)
     assert O.relative_error(y.float().cpu().numpy(), ref) < 1e-3
+
+
+# ---- fused dequant + tcgen05 GEMM (large batch) --------------------------------------------------------------
+def _gpu_ref(x, codes, codebooks, scales, bias):
+    """fp32 reference on the GPU: our dequant kernel (validated against the oracle above) + fp32 matmul."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    W = cuda_kernel.dequant(codes, codebooks, scales).float()
+    y = x.float() @ W.t()
+    return y + bias.float() if bias is not None else y
+
+
+@pytest.mark.parametrize("K,nbits", [(1, 16), (2, 8), (8, 8), (1, 8)])
+@pytest.mark.parametrize("batch", [7, 16, 64, 100, 256, 300])
+def test_tcgen05_gemm_vs_oracle_small(K, nbits, batch):
+    """Sizes the CPU oracle finishes in seconds; in_features % 64 == 0 so the tensor-core kernel is used."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    case = O.make_case(8000 + K + nbits + batch, 512, 200, K, nbits, 8, batch, bias=(batch % 2 == 0))
+    t = to_torch(case, DEV)
+    y = cuda_kernel.matmat_dequant(t["x"], t["codes"], t["codebooks"], t["scales"], t["bias"]).float().cpu().numpy()
+    assert O.relative_error(y, oracle_output(case)) < TOL_FP16_TIGHT
+
+
+@pytest.mark.parametrize("batch", [16, 64, 256])
+@pytest.mark.parametrize("shape", [(4096, 4096), (4096, 14336), (14336, 4096)])
+def test_tcgen05_gemm_full_size_1x16(shape, batch):
+    """BASELINE configs[3]: Llama-3-8B shapes, bs in {16,64,256}, fp16 operands (parity run)."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    fin, fout = shape
+    g = torch.Generator(device=DEV).manual_seed(fin + fout + batch)
+    codes = torch.randint(-32768, 32768, (fout, fin // 8, 1), dtype=torch.int16, device=DEV, generator=g)
+    codebooks = torch.randn((1, 65536, 1, 8), dtype=torch.float16, device=DEV, generator=g)
+    scales = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=DEV, generator=g)).half()
+    x = torch.randn((batch, fin), dtype=torch.float16, device=DEV, generator=g)
+    y = cuda_kernel.matmat_dequant(x, codes, codebooks, scales, None).float()
+    ref = _gpu_ref(x, codes, codebooks, scales, None)
+    rel = ((y - ref).abs().mean() / ref.abs().mean()).item()
+    assert rel < TOL_FP16_TIGHT, rel
+    # deterministic (fixed-order split-K reduction): bitwise identical on a second run
+    y2 = cuda_kernel.matmat_dequant(x, codes, codebooks, scales, None).float()
+    assert torch.equal(y, y2)
+    # gemm op and gemv op agree on the first rows
+    yv = cuda_kernel.matmat(x[:4], codes, codebooks, scales, None).float()
+    assert ((yv - y[:4]).abs().mean() / ref[:4].abs().mean()).item() < 1e-3
+
+
+def test_tcgen05_gemm_bf16_operands():
+    """bf16 operands (the run north_star names): checked against a bf16-fed fp32 reference, bf16 tolerance."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    fin, fout, batch = 4096, 4096, 256
+    g = torch.Generator(device=DEV).manual_seed(5)
+    codes = torch.randint(-32768, 32768, (fout, fin // 8, 1), dtype=torch.int16, device=DEV, generator=g)
+    codebooks = torch.randn((1, 65536, 1, 8), dtype=torch.bfloat16, device=DEV, generator=g)
+    scales = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=DEV, generator=g)).bfloat16()
+    x = torch.randn((batch, fin), dtype=torch.bfloat16, device=DEV, generator=g)
+    y = cuda_kernel.matmat_dequant(x, codes, codebooks, scales, None).float()
+    ref = _gpu_ref(x, codes, codebooks, scales, None)
+    assert ((y - ref).abs().mean() / ref.abs().mean()).item() < TOL_BF16
+
+
+def test_tcgen05_gemm_without_workspace_matches_split():
+    """The C-ABI entry point without a workspace (no split-K) gives the same result up to fp32 summation order."""
+    from aqlm_b200 import _cabi
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    case = O.make_case(8100, 1024, 256, 1, 16, 8, 32, True)
+    t = to_torch(case, DEV)
+    w = cuda_kernel.make_weight(t["codes"], t["codebooks"], t["scales"].reshape(-1), t["bias"])
+    y = torch.empty((32, 256), dtype=torch.float16, device=DEV)
+    _cabi.check(_cabi.lib().aqlm_b200_matmat_dequant(ctypes.byref(w), t["x"].data_ptr(), y.data_ptr(), 32,
+                                                     torch.cuda.current_stream().cuda_stream))
+    assert O.relative_error(y.float().cpu().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
