@@ -271,11 +271,27 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   g.stages = S;
   int ks = 1;
   if (allow_split) {
-    const int tiles = g.m_tiles * g.n_tiles;
-    ks = di->sm_count / tiles;
+    // The kernel is bound by the per-SM codebook-gather rate, so what matters is how many SMs gather.  Model:
+    //   t(ks) = gather_time / sm_efficiency(ks) + split-K fix-up traffic (partials written + read once through L2)
+    const double tiles = (double)g.m_tiles * g.n_tiles;
+    const double gathers = (double)w->out_features * (w->in_features / 8) * K * g.n_tiles;
+    const double t_gather = gathers / 250e9;  // measured chip-wide 16-byte gather rate (profiles/r01/gather_microbench_v1.jsonl)
+    double best = 1e30;
+    const int max_ks = g.total_kblocks / 2 < 16 ? (g.total_kblocks / 2 < 1 ? 1 : g.total_kblocks / 2) : 16;
+    for (int c = 1; c <= max_ks; ++c) {
+      const double ctas = tiles * c;
+      const double waves = (double)((long long)((ctas + di->sm_count - 1) / di->sm_count));
+      const double eff = ctas / (waves * di->sm_count);
+      const double fix = c > 1 ? ctas * g.n_tile * kGemmBlockM * 4.0 * 2.0 / 4e12 : 0.0;
+      const double t = t_gather / eff + fix;
+      if (t < best * 0.97) {  // prefer fewer splits unless the gain is real
+        best = t;
+        ks = c;
+      }
+    }
     const int forced = env_int("AQLM_B200_GEMM_KSPLIT", 0);
     if (forced > 0) ks = forced;
-    if (ks > g.total_kblocks / 2) ks = g.total_kblocks / 2;
+    if (ks > g.total_kblocks) ks = g.total_kblocks;
     if (ks < 1) ks = 1;
   }
   g.ksplit = ks;
@@ -326,6 +342,9 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   p.ksplit = g.ksplit;
   p.n_tile = g.n_tile;
   p.stages = g.stages;
+  p.debug = env_int("AQLM_B200_GEMM_DEBUG", 0);
+  p.codes = w->codes;
+  p.row_bytes = (long long)(w->in_features / 8) * K * CB;
   const size_t smem = gemm_smem_layout(g.stages, g.n_tile).total;
   auto kernel = gemm_dequant_kernel<T, K, CB>;
   static std::atomic<size_t> configured{0};

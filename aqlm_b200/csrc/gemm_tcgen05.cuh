@@ -22,8 +22,8 @@
 
 namespace aqlm_b200 {
 
-constexpr int kGemmThreads = 384;        // warps 0-3: TMA / MMA / TMEM-alloc, then epilogue; warps 4-11: dequant producers
-constexpr int kGemmProducerWarps = 8;
+constexpr int kGemmProducerWarps = 16;
+constexpr int kGemmThreads = 128 + 32 * kGemmProducerWarps;  // warps 0-3: TMA / MMA / TMEM-alloc, then epilogue; warps 4-19: dequant producers
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;          // 64 halves = 128 bytes = one swizzle row
 constexpr int kCodeTileBytes = 128;      // bytes of codes per row per code tile (TMA box inner extent)
@@ -43,6 +43,9 @@ struct GemmParams {
   int ksplit;
   int n_tile;           // N of the MMA (multiple of 16, <= 256)
   int stages;
+  int debug;            // bit0: read codes from global instead of the TMA code tile; bit1: no producer run-ahead
+  const void* codes;    // (debug bit0)
+  long long row_bytes;  // (debug bit0)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -218,60 +221,75 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       }
       umma_commit(tfull_bar);  // accumulator complete
     } else if (warp >= 4) {
-      // ===== dequant producers: 256 threads, thread -> (row, half of the 8 groups of a k-block) =====
+      // ===== dequant producers: 512 threads, thread -> (row, quarter of the 8 groups of a k-block) =====
+      // Software-pipelined: the gathers of k-block i+1 are in flight while k-block i is written to smem.
       const int pt = threadIdx.x - 128;
-      const int row = pt >> 1, gh = pt & 1;
+      const int row = pt >> 2, gq = pt & 3;
       const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
-      constexpr int CB4 = 4 * K * CODE_BYTES;  // code bytes of this thread's 4 groups
-      for (int i = 0; i < nkb; ++i) {
+      constexpr int CB2 = 2 * K * CODE_BYTES;  // code bytes of this thread's 2 groups
+      constexpr int CW = (CB2 + 3) / 4;        // 32-bit words holding them
+      constexpr bool PIPE = (K <= 2);          // double-buffer the gathered vectors when registers allow
+
+      // codes of k-block index i (relative) -> issue the 2*K gathers into wv
+      auto issue = [&](int i, uint4 (&wv)[2][K]) {
         const int kb = kb0 + i;
         const int ct = kb / KB_PER_CTILE, st_in = kb % KB_PER_CTILE;
         const int cs = (ct - ct0) % kCodeTileStages, cit = (ct - ct0) / kCodeTileStages;
         mbar_wait(cfull_bar(cs), cit & 1);
-        // this thread's CB4 code bytes inside the SWIZZLE_128B code tile: logical byte offset -> physical
-        uint32_t cw[CB4 / 4 > 0 ? CB4 / 4 : 1];
-        {
-          const int lbyte = st_in * GB + gh * CB4;  // logical byte in the 128-byte row (CB4-aligned)
-          const uint8_t* crow = gbase + L.codes + cs * kGemmBlockM * kCodeTileBytes + row * 128;
+        uint32_t cw[CW];
+        if (p.debug & 1) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.codes) + (size_t)(m0 + row) * p.row_bytes + (size_t)kb * GB + gq * CB2;
 #pragma unroll
-          for (int q = 0; q < (CB4 + 15) / 16; ++q) {
-            const int lb = lbyte + q * 16;
-            const int chunk = (lb >> 4) ^ (row & 7);
-            const uint8_t* src = crow + (chunk << 4) + (lb & 15);
-            if constexpr (CB4 >= 16) {
-              const uint4 v = *reinterpret_cast<const uint4*>(src);
-              cw[q * 4 + 0] = v.x; cw[q * 4 + 1] = v.y; cw[q * 4 + 2] = v.z; cw[q * 4 + 3] = v.w;
-            } else if constexpr (CB4 == 8) {
-              const uint2 v = *reinterpret_cast<const uint2*>(src);
-              cw[0] = v.x; cw[1] = v.y;
-            } else {
-              cw[0] = *reinterpret_cast<const uint32_t*>(src);
+          for (int q = 0; q < CW; ++q) {
+            uint32_t v = 0;
+            if (m0 + row < p.out_features) {
+              if constexpr (CB2 >= 4) v = reinterpret_cast<const uint32_t*>(src)[q];
+              else v = reinterpret_cast<const uint16_t*>(src)[0];
             }
+            cw[q] = v;
+          }
+        } else {
+          // logical byte offset inside the 128-byte code row -> physical (SWIZZLE_128B: 16-byte chunk ^= row & 7)
+          const int lbyte = st_in * GB + gq * CB2;
+          const uint8_t* crow = gbase + L.codes + cs * kGemmBlockM * kCodeTileBytes + row * 128;
+          if constexpr (CB2 >= 16) {
+            const int chunk = (lbyte >> 4) ^ (row & 7);
+            const uint4 v = *reinterpret_cast<const uint4*>(crow + (chunk << 4));
+            cw[0] = v.x; cw[1] = v.y; cw[2] = v.z; cw[3] = v.w;
+          } else {
+            const int chunk = (lbyte >> 4) ^ (row & 7);
+            const uint8_t* src = crow + (chunk << 4) + (lbyte & 15);
+            if constexpr (CB2 == 8) { const uint2 v = *reinterpret_cast<const uint2*>(src); cw[0] = v.x; cw[1] = v.y; }
+            else if constexpr (CB2 == 4) cw[0] = *reinterpret_cast<const uint32_t*>(src);
+            else cw[0] = *reinterpret_cast<const uint16_t*>(src);
           }
         }
-        // release the code tile after its last k-block (all lanes of the warp have read their bytes)
-        if (st_in == KB_PER_CTILE - 1 || i == nkb - 1) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(cempty_bar(cs));
-        }
-        // gather + additive dequant of 4 groups (issue every gather before any use)
-        uint4 wv[4][K];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 2; ++e) {
 #pragma unroll
           for (int k = 0; k < K; ++k) {
-            const int idx = e * K + k;  // element index among this thread's codes
+            const int idx = e * K + k;
             uint32_t code;
             if constexpr (CODE_BYTES == 2) code = (cw[idx >> 1] >> ((idx & 1) * 16)) & 0xffffu;
             else code = (cw[idx >> 2] >> ((idx & 3) * 8)) & 0xffu;
             wv[e][k] = ld_gather_v4<0>(gcb + (((size_t)k << p.nbits) + code));
           }
         }
+        // Release the code tile after its last k-block.  This MUST come after the gathers above were issued: their
+        // addresses depend on the code registers, so the shared-memory loads of the codes have completed by now.
+        // (Releasing right after issuing those loads lets the TMA refill the slot while they are still in flight.)
+        if (st_in == KB_PER_CTILE - 1 || i == nkb - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(cempty_bar(cs));
+        }
+      };
+      // additive dequant + write the 2 groups of k-block i into the swizzled A stage, then signal the MMA thread
+      auto commit = [&](int i, uint4 (&wv)[2][K]) {
         const int s = i % S, it = i / S;
         if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
         uint8_t* arow = gbase + L.a + s * kGemmBlockM * 128 + row * 128;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 2; ++e) {
           uint4 v = wv[e][0];
           if constexpr (K > 1) {
             float f[8];
@@ -281,24 +299,44 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             v.x = DT<T>::pack2(f[0], f[1]); v.y = DT<T>::pack2(f[2], f[3]);
             v.z = DT<T>::pack2(f[4], f[5]); v.w = DT<T>::pack2(f[6], f[7]);
           }
-          const int j = gh * 4 + e;  // 16-byte chunk (= group) index inside the 128-byte K row
+          const int j = gq * 2 + e;  // 16-byte chunk (= group) index inside the 128-byte K row
           *reinterpret_cast<uint4*>(arow + ((j ^ (row & 7)) << 4)) = v;
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(s));
+      };
+      if constexpr (PIPE) {
+        uint4 w0[2][K], w1[2][K];
+        issue(0, w0);
+        for (int i = 0; i < nkb; i += 2) {
+          if (i + 1 < nkb) issue(i + 1, w1);
+          commit(i, w0);
+          if (i + 1 < nkb) {
+            if (i + 2 < nkb) issue(i + 2, w0);
+            commit(i + 1, w1);
+          }
+        }
+      } else {
+        uint4 w0[2][K];
+        for (int i = 0; i < nkb; ++i) {
+          issue(i, w0);
+          commit(i, w0);
+        }
       }
     }
   }
 
   // ===== epilogue: warps 0-3, thread <-> TMEM lane <-> output row =====
+  const size_t tile_id = (size_t)m_tile * gridDim.z + n_blk;
+  T* y = reinterpret_cast<T*>(p.y);
   if (warp < 4) {
     __syncwarp();  // lanes 1-31 of the TMA / MMA warps wait here for their lane 0 (tcgen05.ld is warp-collective)
     const int row_in_tile = warp * 32 + lane;
     const int row = m0 + row_in_tile;
     const bool row_ok = row < p.out_features;
     float sc = 1.f, bi = 0.f;
-    if (row_ok) {
+    if (row_ok && p.ksplit == 1) {
       sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
       if (p.bias) bi = DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]);
     }
@@ -306,8 +344,6 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
     }
-    T* y = reinterpret_cast<T*>(p.y);
-    const size_t tile_id = (size_t)m_tile * gridDim.z + n_blk;
     float* my_part = p.ws_partials ? p.ws_partials + ((tile_id * p.ksplit + split) * (size_t)N) * kGemmBlockM : nullptr;
     for (int c0 = 0; c0 < N; c0 += 32) {
       uint32_t r[32];
@@ -329,26 +365,45 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           if (c0 + c < N) my_part[(size_t)(c0 + c) * kGemmBlockM + row_in_tile] = __uint_as_float(r[c]);
       }
     }
-    if (p.ksplit > 1) {
-      // last-arriving split of this tile reduces all partials in split order (deterministic) and stores y
+  }
+  if (p.ksplit > 1) {
+    // Split-K fix-up: the LAST-arriving split of this tile adds all partials in split order (deterministic) with the
+    // whole CTA: thread -> (row, column phase); partials are [split][column][128 rows] so warps read 512 contiguous bytes.
+    __threadfence();
+    __syncthreads();
+    uint32_t* flag = reinterpret_cast<uint32_t*>(gbase + L.flag);
+    if (threadIdx.x == 0) {
+      const unsigned int old = atomicAdd(p.ws_counters + tile_id, 1u);
+      const bool last = (old == (unsigned int)p.ksplit - 1);
+      *flag = last ? 1u : 0u;
+      if (last) p.ws_counters[tile_id] = 0u;  // leave the counter clean for the next call
+    }
+    __syncthreads();
+    if (*flag) {
       __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      uint32_t* flag = reinterpret_cast<uint32_t*>(gbase + L.flag);
-      if (threadIdx.x == 0) {
-        const unsigned int old = atomicAdd(p.ws_counters + tile_id, 1u);
-        *flag = (old == (unsigned int)p.ksplit - 1) ? 1u : 0u;
-        if (old == (unsigned int)p.ksplit - 1) p.ws_counters[tile_id] = 0u;  // leave the counter clean for the next call
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*flag) {
-        __threadfence();
-        const float* parts = p.ws_partials + (tile_id * p.ksplit) * (size_t)N * kGemmBlockM;
-        for (int c = 0; c < N; ++c) {
-          const int n = n0 + c;
-          if (n >= p.batch) break;
-          float v = 0.f;
-          for (int sp = 0; sp < p.ksplit; ++sp) v += __ldcg(parts + ((size_t)sp * N + c) * kGemmBlockM + row_in_tile);
-          if (row_ok) y[(size_t)n * p.out_features + row] = DT<T>::from_float(fmaf(v, sc, bi));
+      const float* parts = p.ws_partials + (tile_id * p.ksplit) * (size_t)N * kGemmBlockM;
+      const int rrow = threadIdx.x & (kGemmBlockM - 1);
+      const int cphase = threadIdx.x >> 7;
+      constexpr int kPhases = kGemmThreads / kGemmBlockM;
+      const int row = m0 + rrow;
+      if (row < p.out_features) {
+        const float sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+        const float bi = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
+        const int ncols = min(N, p.batch - n0);
+        for (int c = cphase; c < ncols; c += kPhases * 4) {
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int sp = 0; sp < p.ksplit; ++sp) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int cc = c + u * kPhases;
+              if (cc < ncols) v[u] += __ldcg(parts + ((size_t)sp * N + cc) * kGemmBlockM + rrow);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int cc = c + u * kPhases;
+            if (cc < ncols) y[(size_t)(n0 + cc) * p.out_features + row] = DT<T>::from_float(fmaf(v[u], sc, bi));
+          }
         }
       }
     }

@@ -86,7 +86,9 @@ def main():
                         fns = [(lambda w=w: op(x, w[0], w[1], w[2], None)) for w in ws]
                         us = time_graph(fns)
                         gbs = cbytes / us / 1e3
-                        row = dict(scheme=scheme, in_features=fin, out_features=fout, batch=batch, gather_mode=int(mode),
+                        tflops = 2.0 * batch * fin * fout / us / 1e6
+                        row = dict(scheme=scheme, in_features=fin, out_features=fout, batch=batch, tflops=round(tflops, 1),
+                                   gather_mode=int(mode),
                                    ctas_per_sm=int(ctas), op=args.op, us=round(us, 3), code_GBps=round(gbs, 1),
                                    frac_of_hbm_peak=round(gbs / peak, 4), peak=peak_kind, rotating_copies=copies)
                         rows.append(row)
