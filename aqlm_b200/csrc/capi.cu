@@ -238,9 +238,11 @@ static tmap_encode_fn get_tmap_encode() {
   return fn;
 }
 
+constexpr int kGemmMaxTiles = 16384;
+
 struct GemmPlan {
   bool ok = false;       // tcgen05 path applicable
-  int m_tiles = 0, n_tiles = 0, n_tile = 0, ksplit = 1, stages = 0, total_kblocks = 0;
+  int m_tiles = 0, n_tiles = 0, n_tile = 0, ksplit = 1, stages = 0, total_kblocks = 0, cluster = 1;
   size_t counters_bytes = 0, partials_bytes = 0;
 };
 
@@ -294,8 +296,16 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
     if (ks > g.total_kblocks) ks = g.total_kblocks;
     if (ks < 1) ks = 1;
   }
+  // fixed-size counter region (the partials of one plan must never overlap the counters of another plan that
+  // reuses the same persistent workspace)
+  g.counters_bytes = kGemmMaxTiles * 4;
+  if ((size_t)g.m_tiles * g.n_tiles > (size_t)kGemmMaxTiles) ks = 1;
   g.ksplit = ks;
-  g.counters_bytes = (((size_t)g.m_tiles * g.n_tiles * 4) + 255) & ~(size_t)255;
+  // X-tile multicast: CTAs of a cluster (consecutive M tiles, same K range) each TMA-load 1/C of the X tile and
+  // multicast it to all C, cutting the L2->SM traffic of X by C.
+  int cl = env_int("AQLM_B200_GEMM_CLUSTER", 1);  // measured: no gain (the limit is per-SM L2->SM ingest), kept for experiments
+  while (cl > 1 && (g.m_tiles % cl != 0 || g.n_tile % (8 * cl) != 0)) cl >>= 1;
+  g.cluster = cl < 1 ? 1 : cl;
   g.partials_bytes = ks > 1 ? (size_t)g.m_tiles * g.n_tiles * ks * g.n_tile * kGemmBlockM * 4 : 0;
   g.ok = true;
   return g;
@@ -310,7 +320,7 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   {
     cuuint64_t dims[2] = {(cuuint64_t)w->in_features, (cuuint64_t)batch};
     cuuint64_t strides[1] = {(cuuint64_t)w->in_features * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)g.n_tile};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)(g.n_tile / g.cluster)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&tx, DT<T>::is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                      const_cast<void*>(input), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -342,6 +352,7 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   p.ksplit = g.ksplit;
   p.n_tile = g.n_tile;
   p.stages = g.stages;
+  p.cluster = g.cluster;
   p.debug = env_int("AQLM_B200_GEMM_DEBUG", 0);
   p.codes = w->codes;
   p.row_bytes = (long long)(w->in_features / 8) * K * CB;
@@ -352,9 +363,20 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
     AQLM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured.store(smem, std::memory_order_relaxed);
   }
-  kernel<<<dim3(g.m_tiles, g.ksplit, g.n_tiles), kGemmThreads, smem, st>>>(tx, tc, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.m_tiles, g.ksplit, g.n_tiles);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = g.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tx, tc, p));
   count_launch();
-  AQLM_CUDA_CHECK(cudaGetLastError());
   return AQLM_B200_OK;
 }
 

@@ -43,6 +43,7 @@ struct GemmParams {
   int ksplit;
   int n_tile;           // N of the MMA (multiple of 16, <= 256)
   int stages;
+  int cluster;          // CTAs per cluster along M that share (multicast) the X tiles
   int debug;            // bit0: read codes from global instead of the TMA code tile; bit1: no producer run-ahead
   const void* codes;    // (debug bit0)
   long long row_bytes;  // (debug bit0)
@@ -68,6 +69,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -141,6 +158,9 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const GemmSmem L = gemm_smem_layout(p.stages, p.n_tile);
   const int S = p.stages;
   const int N = p.n_tile;
+  const int C = p.cluster;
+  const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, split = blockIdx.y, n_blk = blockIdx.z;
@@ -163,7 +183,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), kGemmProducerWarps + 1);  // 8 producer warps + the TMA thread (expect_tx)
-      mbar_init(empty_bar(s), 1);                      // tcgen05.commit
+      mbar_init(empty_bar(s), C);                      // tcgen05.commit of every CTA in the cluster
     }
     for (int s = 0; s < kCodeTileStages; ++s) {
       mbar_init(cfull_bar(s), 1);
@@ -180,6 +200,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -198,8 +219,16 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S, it = i / S;
         if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
-        mbar_expect_tx(full_bar(s), (uint32_t)N * 128);
-        tma_load_2d(base + L.b + s * N * 128, &tmap_x, (kb0 + i) * kGemmBlockK, n0, full_bar(s));
+        mbar_expect_tx(full_bar(s), (uint32_t)N * 128);  // all C slices land here
+        if (C == 1) {
+          tma_load_2d(base + L.b + s * N * 128, &tmap_x, (kb0 + i) * kGemmBlockK, n0, full_bar(s));
+        } else {
+          // this CTA fetches rows [crank*N/C, (crank+1)*N/C) of the X tile and multicasts them to the whole cluster;
+          // empty_bar(s) (count C) guarantees every CTA of the cluster has released stage s
+          const int rows = N / C;
+          tma_load_2d_mc(base + L.b + s * N * 128 + crank * rows * 128, &tmap_x, (kb0 + i) * kGemmBlockK, n0 + crank * rows,
+                         full_bar(s), cmask);
+        }
         // prefetch the NEXT code tile while the producers work on the current one
         const int ct_cur = (kb0 + i) / KB_PER_CTILE;
         if (ct_loaded < ct1 && ct_loaded <= ct_cur + 1) load_ctile(ct_loaded++);
@@ -217,7 +246,9 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         for (int k = 0; k < kGemmBlockK / 16; ++k) {
           umma_f16(tmem_base, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc, (i | k) ? 1u : 0u);
         }
-        umma_commit(empty_bar(s));  // frees this smem stage when the MMAs above have read it
+        // frees this smem stage (in every CTA of the cluster) when the MMAs above have read it
+        if (C == 1) umma_commit(empty_bar(s));
+        else umma_commit_mc(empty_bar(s), cmask);
       }
       umma_commit(tfull_bar);  // accumulator complete
     } else if (warp >= 4) {
@@ -410,6 +441,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();  // no CTA exits while a peer can still signal its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }

@@ -37,9 +37,9 @@ def run(fin, fout, batch, reps=3, label=""):
 
 
 if __name__ == "__main__":
-    for env in ({}, {"AQLM_B200_GEMM_DEBUG": "1"}, {"AQLM_B200_GEMM_DEBUG": "2"}, {"AQLM_B200_GEMM_DEBUG": "3"}):
+    for env in ({}, {"AQLM_B200_GEMM_KSPLIT": "1"}, {"AQLM_B200_GEMM_KSPLIT": "2"}, {"AQLM_B200_GEMM_KSPLIT": "5"}):
         for k in ("AQLM_B200_GEMM_STAGES", "AQLM_B200_GEMM_KSPLIT", "AQLM_B200_GEMM_DEBUG"):
             os.environ.pop(k, None)
         os.environ.update(env)
-        run(4096, 14336, 256, reps=4, label=str(env))
-        run(14336, 4096, 256, reps=4, label=str(env))
+        run(4096, 14336, 16, reps=3, label=str(env))
+        run(4096, 4096, 16, reps=2, label=str(env))
