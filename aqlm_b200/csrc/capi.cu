@@ -9,6 +9,7 @@
 #include "dequant.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemv.cuh"
+#include "gemv_lut.cuh"
 
 namespace aqlm_b200 {
 
@@ -221,6 +222,92 @@ static int dequant_typed(const aqlm_b200_weight_t* w, void* out, int apply_scale
   return AQLM_B200_OK;
 }
 
+// ---- Kx8 LUT GEMV: host side ------------------------------------------------------------------------
+struct LutPlan {
+  bool ok = false;
+  int J = 32, n_slabs = 0, row_blocks = 0, rows_per_block = 0;
+  size_t smem = 0, partials_bytes = 0;
+};
+constexpr size_t kWsCountersBytes = 65536;  // fixed counter region at the head of every workspace (16384 tickets)
+
+static LutPlan lut_plan(const aqlm_b200_weight_t* w, int64_t batch, const DeviceInfo* di) {
+  LutPlan L;
+  const int K = w->num_codebooks;
+  if (batch != 1 || w->nbits_per_codebook != 8 || w->in_group_size != 8) return L;
+  if (!(K == 1 || K == 2 || K == 4 || K == 8)) return L;
+  if (env_int("AQLM_B200_DISABLE_LUT", 0)) return L;
+  if ((reinterpret_cast<uintptr_t>(w->codes) & 7) != 0) return L;
+  L.J = (K == 8) ? 16 : 32;
+  const int in_groups = (int)(w->in_features / 8);
+  L.n_slabs = (in_groups + L.J - 1) / L.J;
+  L.smem = (size_t)K * 256 * L.J * 4;
+  if (L.smem + 1024 > (size_t)di->max_smem_optin) return L;
+  int per_sm = (int)((size_t)di->max_smem_optin / (L.smem + 1024));
+  const int want = env_int("AQLM_B200_LUT_CTAS_PER_SM", 2);
+  if (per_sm > want) per_sm = want;
+  if (per_sm < 1) per_sm = 1;
+  int rb = (di->sm_count * per_sm + L.n_slabs - 1) / L.n_slabs;
+  if (rb < 1) rb = 1;
+  int rpb = (int)((w->out_features + rb - 1) / rb);
+  rpb = (rpb + 31) / 32 * 32;
+  L.rows_per_block = rpb;
+  L.row_blocks = (int)((w->out_features + rpb - 1) / rpb);
+  if ((size_t)L.row_blocks * 4 > kWsCountersBytes) return L;
+  L.partials_bytes = (size_t)L.n_slabs * w->out_features * 4;
+  L.ok = true;
+  return L;
+}
+
+template <typename T, int K, int J>
+static int launch_lut(const aqlm_b200_weight_t* w, const void* input, void* output, uint32_t flags, const LutPlan& L,
+                      void* workspace, cudaStream_t st) {
+  LutParams p;
+  p.codes = w->codes;
+  p.codebooks = w->codebooks;
+  p.scales = w->scales;
+  p.bias = w->bias;
+  p.x = input;
+  p.y = output;
+  p.ws_counters = reinterpret_cast<unsigned int*>(workspace);
+  p.ws_partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kWsCountersBytes);
+  p.out_features = (int)w->out_features;
+  p.in_groups = (int)(w->in_features / 8);
+  p.n_slabs = L.n_slabs;
+  p.rows_per_block = L.rows_per_block;
+  p.partial_f32 = (flags & AQLM_B200_FLAG_PARTIAL_F32) ? 1 : 0;
+  auto kernel = gemv_lut_kernel<T, K, J>;
+  static std::atomic<size_t> configured{0};
+  if (configured.load(std::memory_order_relaxed) < L.smem) {
+    int rc = set_smem(kernel, L.smem);
+    if (rc) return rc;
+    configured.store(L.smem, std::memory_order_relaxed);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(L.n_slabs, L.row_blocks);
+  cfg.blockDim = dim3(kLutThreads);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = env_int("AQLM_B200_PDL", 1) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
+  count_launch();
+  return AQLM_B200_OK;
+}
+
+template <typename T>
+static int lut_typed(const aqlm_b200_weight_t* w, const void* input, void* output, uint32_t flags, const LutPlan& L,
+                     void* workspace, cudaStream_t st) {
+  switch (w->num_codebooks) {
+    case 1: return launch_lut<T, 1, 32>(w, input, output, flags, L, workspace, st);
+    case 2: return launch_lut<T, 2, 32>(w, input, output, flags, L, workspace, st);
+    case 4: return launch_lut<T, 4, 32>(w, input, output, flags, L, workspace, st);
+    default: return launch_lut<T, 8, 16>(w, input, output, flags, L, workspace, st);
+  }
+}
+
 // ---- fused dequant + tcgen05 GEMM: host side ------------------------------------------------------
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -298,7 +385,7 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   }
   // fixed-size counter region (the partials of one plan must never overlap the counters of another plan that
   // reuses the same persistent workspace)
-  g.counters_bytes = kGemmMaxTiles * 4;
+  g.counters_bytes = kWsCountersBytes;
   if ((size_t)g.m_tiles * g.n_tiles > (size_t)kGemmMaxTiles) ks = 1;
   g.ksplit = ks;
   // X-tile multicast: CTAs of a cluster (consecutive M tiles, same K range) each TMA-load 1/C of the X tile and
@@ -435,6 +522,32 @@ int aqlm_b200_matmat_ex(const aqlm_b200_weight_t* w, const void* input, void* ou
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (w->dtype == AQLM_B200_F16) return matmat_typed<__half>(w, input, output, batch, flags, di, st);
   return matmat_typed<__nv_bfloat16>(w, input, output, batch, flags, di, st);
+}
+
+size_t aqlm_b200_matmat_workspace_bytes(const aqlm_b200_weight_t* w, int64_t batch) {
+  if (validate(w, false) != AQLM_B200_OK || batch <= 0) return 0;
+  const DeviceInfo* di = device_info();
+  if (!di) return 0;
+  const LutPlan L = lut_plan(w, batch, di);
+  return L.ok ? kWsCountersBytes + L.partials_bytes : 0;
+}
+
+int aqlm_b200_matmat_ws(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, uint32_t flags,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  const bool partial = (flags & AQLM_B200_FLAG_PARTIAL_F32) != 0;
+  int rc = validate(w, !partial);
+  if (rc) return rc;
+  if (batch == 1 && workspace && input && output && (reinterpret_cast<uintptr_t>(input) & 3) == 0) {
+    const DeviceInfo* di = device_info();
+    if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
+    const LutPlan L = lut_plan(w, batch, di);
+    if (L.ok && workspace_bytes >= kWsCountersBytes + L.partials_bytes) {
+      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+      if (w->dtype == AQLM_B200_F16) return lut_typed<__half>(w, input, output, flags, L, workspace, st);
+      return lut_typed<__nv_bfloat16>(w, input, output, flags, L, workspace, st);
+    }
+  }
+  return aqlm_b200_matmat_ex(w, input, output, batch, flags, stream);
 }
 
 int aqlm_b200_matmat(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, void* stream) {

@@ -1,0 +1,193 @@
+// Batch-1 GEMV for 256-entry codebooks (Kx8 schemes: 1x8, 2x8, 4x8, 8x8), dot-product LUT formulation.
+//
+//   y[o] = scale[o] * sum_j sum_k L[j][k][code[o,j,k]],     L[j][k][c] = codebook[k][c] . x_j   (fp32)
+//
+// Replaces Code2x8MatVec / CodeKx8MatVec (reference cuda_kernel.cu:144-233, 296-390) and the Triton kernel the
+// reference uses for 8x8 (kernel_selector.py:91-94).  The reference's direct kernels gather a 16-byte codebook
+// vector per code from shared memory (8x replicated to dodge bank conflicts, cuda_kernel.cu:168-173) and do 8
+// FMAs per code; its CPU kernel (numba_kernel.py:37-48) uses the LUT idea.  Here every code byte costs ONE
+// conflict-free 4-byte shared-memory read and one add:
+//   * a CTA owns a slab of J in-groups (J = 32, or 16 for K = 8) and a block of output rows;
+//   * the LUT [K][256][J] fp32 is built in shared memory by tensor cores (mma.sync m16n8k8, exact fp16/bf16
+//     products, fp32 accumulate) and stored so that lane <-> group <-> bank: lookups never conflict for J = 32;
+//   * each lane streams the K code bytes of ITS group for 32 rows (coalesced 64-byte row segments, all loads in
+//     flight), looks them up, and a 31-shuffle transpose-reduce leaves lane l with the total of row l;
+//   * per-slab partial rows go to an fp32 workspace; the LAST CTA of a row block (atomic ticket) adds the slabs
+//     in a fixed order and applies scale + bias (deterministic, no float atomics).
+#pragma once
+
+#include "common.cuh"
+
+namespace aqlm_b200 {
+
+struct LutParams {
+  const void* codes;
+  const void* codebooks;
+  const void* scales;
+  const void* bias;
+  const void* x;       // [in_features]
+  void* y;             // [out_features] T, or float when partial_f32
+  float* ws_partials;  // [n_slabs][out_features]
+  unsigned int* ws_counters;  // [row_blocks], zero on entry, left zero
+  int out_features;
+  int in_groups;
+  int n_slabs;
+  int rows_per_block;  // multiple of 32
+  int partial_f32;
+};
+
+constexpr int kLutThreads = 256;
+
+__device__ __forceinline__ void mma_m16n8k8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0, bool bf16) {
+  if (bf16) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+  }
+}
+
+// K codebooks, J groups per slab (32 -> one row per warp step, 16 -> two rows per warp step)
+template <typename T, int K, int J>
+__global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p) {
+  extern __shared__ __align__(16) float lut[];  // [K][256][J]
+  constexpr int NT = J / 8;                     // n-tiles (8 groups each) per slab
+  constexpr int RPW = 32 / J;                   // rows per warp step
+  constexpr int kWarps = kLutThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slab = blockIdx.x, rb = blockIdx.y;
+  const int j0 = slab * J;
+  griddep_launch_dependents();
+  griddep_wait();  // x is produced by the previous kernel
+
+  // ---------------- LUT build: D[16 entries x 8 groups] = CB[16 x 8] . X^T[8 x 8], tensor cores ----------------
+  {
+    const int q = lane >> 2, m = lane & 3;
+    // B fragments: column n = q of n-tile t  <->  group j0 + (J/4)*(q>>1)... see mapping below; k = 2m, 2m+1
+    // column (2m'+i) of n-tile t holds group  (2*NT)*m' + 2t + i  so that a lane ends up with 2*NT consecutive groups
+    uint32_t bfrag[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int g = j0 + (2 * NT) * (q >> 1) + 2 * t + (q & 1);
+      uint32_t v = 0;
+      if (g < p.in_groups) v = reinterpret_cast<const uint32_t*>(p.x)[g * 4 + m];
+      bfrag[t] = v;
+    }
+    const uint32_t* cb32 = reinterpret_cast<const uint32_t*>(p.codebooks);
+    for (int mt = warp; mt < K * 16; mt += kWarps) {  // 16-entry tiles over all K codebooks
+      const int e0 = mt * 16;                          // global entry index (k*256 + c)
+      const uint32_t a0 = cb32[(size_t)(e0 + q) * 4 + m];
+      const uint32_t a1 = cb32[(size_t)(e0 + q + 8) * 4 + m];
+      float d[NT][4];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        d[t][0] = d[t][1] = d[t][2] = d[t][3] = 0.f;
+        mma_m16n8k8(d[t], a0, a1, bfrag[t], DT<T>::is_bf16);
+      }
+      // lane holds, for entry e0+q, groups (2NT)m .. (2NT)m + 2NT-1 in d[t][0..1]; for entry e0+q+8 in d[t][2..3]
+      float* r0 = lut + (size_t)(e0 + q) * J + (2 * NT) * m;
+      float* r1 = lut + (size_t)(e0 + q + 8) * J + (2 * NT) * m;
+      if constexpr (NT == 4) {
+        // two 16-byte stores per entry; odd rows store the upper half first so that a quarter-warp hits 32 distinct banks
+        const bool odd = q & 1;
+        float4 lo0 = make_float4(d[0][0], d[0][1], d[1][0], d[1][1]), hi0 = make_float4(d[2][0], d[2][1], d[3][0], d[3][1]);
+        float4 lo1 = make_float4(d[0][2], d[0][3], d[1][2], d[1][3]), hi1 = make_float4(d[2][2], d[2][3], d[3][2], d[3][3]);
+        *reinterpret_cast<float4*>(r0 + (odd ? 4 : 0)) = odd ? hi0 : lo0;
+        *reinterpret_cast<float4*>(r0 + (odd ? 0 : 4)) = odd ? lo0 : hi0;
+        *reinterpret_cast<float4*>(r1 + (odd ? 4 : 0)) = odd ? hi1 : lo1;
+        *reinterpret_cast<float4*>(r1 + (odd ? 0 : 4)) = odd ? lo1 : hi1;
+      } else {
+        // J = 16: one 16-byte store per entry; consecutive entries alternate bank halves
+        *reinterpret_cast<float4*>(r0) = make_float4(d[0][0], d[0][1], d[1][0], d[1][1]);
+        *reinterpret_cast<float4*>(r1) = make_float4(d[0][2], d[0][3], d[1][2], d[1][3]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- lookups: lane <-> group, 32/RPW... rows in flight per warp ----------------
+  const int jj = lane & (J - 1);
+  const int rsub = lane / J;  // 0 for J == 32; 0/1 for J == 16
+  const int g = j0 + jj;
+  const bool g_ok = g < p.in_groups;
+  const size_t row_bytes = (size_t)p.in_groups * K;
+  const uint8_t* cbase = reinterpret_cast<const uint8_t*>(p.codes) + (size_t)g * K;
+  const float* lbase = lut + jj;
+  const int row_begin = rb * p.rows_per_block;
+  const int row_end = min(p.out_features, row_begin + p.rows_per_block);
+  constexpr int RB = J;  // rows per lane-batch (each lane accumulates RB values, the butterfly leaves one row per lane)
+  float* part = p.ws_partials + (size_t)slab * p.out_features;
+
+  for (int r0 = row_begin + warp * (RB * RPW); r0 < row_end; r0 += kWarps * RB * RPW) {
+    float v[RB];
+    // all code loads of the batch first (RB independent loads in flight per lane)
+    uint32_t cw[RB][(K + 3) / 4];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int row = r0 + i * RPW + rsub;
+      const bool ok = g_ok && row < row_end;
+      const uint8_t* src = cbase + (size_t)row * row_bytes;
+      if constexpr (K == 1) cw[i][0] = ok ? (uint32_t)__ldg(src) : 0u;
+      else if constexpr (K == 2) cw[i][0] = ok ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(src)) : 0u;
+      else if constexpr (K == 4) cw[i][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
+      else {
+        uint2 t2 = ok ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0u, 0u);
+        cw[i][0] = t2.x; cw[i][1] = t2.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int row = r0 + i * RPW + rsub;
+      float acc = 0.f;
+      if (g_ok && row < row_end) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const uint32_t c = (cw[i][k >> 2] >> ((k & 3) * 8)) & 0xffu;
+          acc += lbase[(size_t)(k * 256 + c) * J];
+        }
+      }
+      v[i] = acc;
+    }
+    // transpose-reduce over the J lanes of a row group: lane jj ends with the total of row index jj of the batch
+#pragma unroll
+    for (int d = J / 2, n = RB; d >= 1; d >>= 1, n >>= 1) {
+      const bool up = (lane & d) != 0;
+#pragma unroll
+      for (int i = 0; i < n / 2; ++i) {
+        const float send = up ? v[i] : v[i + n / 2];
+        const float keep = up ? v[i + n / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+      }
+    }
+    const int row = r0 + jj * RPW + rsub;
+    if (row < row_end) part[row] = v[0];
+  }
+
+  // ---------------- fix-up: the last slab CTA of this row block adds the slabs in order ----------------
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last;
+  if (tid == 0) {
+    const unsigned int old = atomicAdd(p.ws_counters + rb, 1u);
+    s_last = (old == (unsigned int)p.n_slabs - 1) ? 1u : 0u;
+    if (s_last) p.ws_counters[rb] = 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int row = row_begin + tid; row < row_end; row += kLutThreads) {
+      float acc = 0.f;
+      for (int s = 0; s < p.n_slabs; ++s) acc += __ldcg(p.ws_partials + (size_t)s * p.out_features + row);
+      if (p.partial_f32) {
+        reinterpret_cast<float*>(p.y)[row] = acc;
+      } else {
+        const float sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+        const float bi = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
+        reinterpret_cast<T*>(p.y)[row] = DT<T>::from_float(fmaf(acc, sc, bi));
+      }
+    }
+  }
+}
+
+}  // namespace aqlm_b200

@@ -101,58 +101,57 @@ class _on_device:
             self.ctx.__exit__(*exc)
 
 
-def _matmat_impl(entry: str, input: torch.Tensor, codes: torch.Tensor, codebooks: torch.Tensor,
-                 scales: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    device = _require_cuda(input, codes, codebooks, scales, bias)
-    _dtype_code(input)
-    if input.dtype != codebooks.dtype:
-        raise ValueError(f"input dtype {input.dtype} != codebooks dtype {codebooks.dtype}")
-    scales_flat = scales.reshape(-1)
-    w = make_weight(codes, codebooks, scales_flat, bias)
-    if input.shape[-1] != w.in_features:
-        raise ValueError(f"input has {input.shape[-1]} features, weight expects {w.in_features}")
-    flat_input = input.reshape(-1, input.shape[-1])
-    if not flat_input.is_contiguous():
-        flat_input = flat_input.contiguous()
-    batch = flat_input.shape[0]
-    flat_output = torch.empty((batch, w.out_features), dtype=input.dtype, device=device)
-    with _on_device(device):
-        fn = getattr(_cabi.lib(), entry)
-        _cabi.check(fn(ctypes.byref(w), flat_input.data_ptr(), flat_output.data_ptr(), batch, _stream_ptr(device)))
-    return flat_output.reshape(input.shape[:-1] + (w.out_features,))
-
-
-def matmat(input, codes, codebooks, scales, bias=None) -> torch.Tensor:
-    """Fused gather + additive dequant + GEMV (+scale+bias), any scheme; for small batch."""
-    return _matmat_impl("aqlm_b200_matmat", input, codes, codebooks, scales, bias)
-
-
-_WORKSPACES: dict = {}  # (device index) -> persistent zero-initialised split-K workspace (counters stay zero)
+_WORKSPACES: dict = {}  # device index -> persistent zero-initialised workspace (ticket counters stay zero)
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Persistent per-device workspace for the split-K GEMM.  The kernel leaves the tile counters at zero, so the
-    buffer is zeroed only when it is (re)allocated.  One workspace per device: concurrent use from several streams
-    of the same device is not supported."""
+    """Persistent per-device workspace for the split-K GEMM and the LUT GEMV.  The kernels leave the ticket counters at
+    zero, so the buffer is zeroed only when it is (re)allocated.  One workspace per device: concurrent use from several
+    streams of the same device is not supported."""
     ws = _WORKSPACES.get(device.index)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        ws = torch.zeros(max(nbytes, 4 << 20), dtype=torch.uint8, device=device)
         _WORKSPACES[device.index] = ws
     return ws
 
 
-def matmat_dequant(input, codes, codebooks, scales, bias=None) -> torch.Tensor:
-    """Fused dequant + tcgen05 tensor-core GEMM (+scale+bias); for large batch (reference `*_matmat_dequant`)."""
+def _prepare(input, codes, codebooks, scales, bias):
     device = _require_cuda(input, codes, codebooks, scales, bias)
     _dtype_code(input)
     if input.dtype != codebooks.dtype:
         raise ValueError(f"input dtype {input.dtype} != codebooks dtype {codebooks.dtype}")
-    w = make_weight(codes, codebooks, scales.reshape(-1), bias)
+    w = make_weight(codes, codebooks, scales.reshape(-1) if scales is not None else None, bias)
     if input.shape[-1] != w.in_features:
         raise ValueError(f"input has {input.shape[-1]} features, weight expects {w.in_features}")
     flat_input = input.reshape(-1, input.shape[-1])
     if not flat_input.is_contiguous():
         flat_input = flat_input.contiguous()
+    return device, w, flat_input
+
+
+def _call_matmat_ws(device, w, flat_input, flat_output, flags: int) -> None:
+    batch = flat_input.shape[0]
+    with _on_device(device):
+        L = _cabi.lib()
+        need = L.aqlm_b200_matmat_workspace_bytes(ctypes.byref(w), batch) if batch > 0 else 0
+        ws = _workspace(device, need) if need else None
+        _cabi.check(L.aqlm_b200_matmat_ws(ctypes.byref(w), flat_input.data_ptr(), flat_output.data_ptr(), batch, flags,
+                                          ws.data_ptr() if ws is not None else None,
+                                          ws.numel() if ws is not None else 0, _stream_ptr(device)))
+
+
+def matmat(input, codes, codebooks, scales, bias=None) -> torch.Tensor:
+    """Fused gather + additive dequant + GEMV (+scale+bias), any scheme; for small batch (reference `*_matmat`).
+    Batch-1 calls on 256-entry codebooks run the dot-product-LUT kernel."""
+    device, w, flat_input = _prepare(input, codes, codebooks, scales, bias)
+    flat_output = torch.empty((flat_input.shape[0], w.out_features), dtype=input.dtype, device=device)
+    _call_matmat_ws(device, w, flat_input, flat_output, 0)
+    return flat_output.reshape(input.shape[:-1] + (w.out_features,))
+
+
+def matmat_dequant(input, codes, codebooks, scales, bias=None) -> torch.Tensor:
+    """Fused dequant + tcgen05 tensor-core GEMM (+scale+bias); for large batch (reference `*_matmat_dequant`)."""
+    device, w, flat_input = _prepare(input, codes, codebooks, scales, bias)
     batch = flat_input.shape[0]
     flat_output = torch.empty((batch, w.out_features), dtype=input.dtype, device=device)
     with _on_device(device):
@@ -171,9 +170,7 @@ def matmat_partial(input, codes, codebooks) -> torch.Tensor:
     w = make_weight(codes, codebooks, None, None)
     flat_input = input.reshape(-1, input.shape[-1]).contiguous()
     out = torch.empty((flat_input.shape[0], w.out_features), dtype=torch.float32, device=device)
-    with _on_device(device):
-        _cabi.check(_cabi.lib().aqlm_b200_matmat_ex(ctypes.byref(w), flat_input.data_ptr(), out.data_ptr(),
-                                                    flat_input.shape[0], _cabi.FLAG_PARTIAL_F32, _stream_ptr(device)))
+    _call_matmat_ws(device, w, flat_input, out, _cabi.FLAG_PARTIAL_F32)
     return out
 
 

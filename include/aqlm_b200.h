@@ -76,6 +76,13 @@ int aqlm_b200_matmat(const aqlm_b200_weight_t* w, const void* input, void* outpu
 int aqlm_b200_matmat_ex(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, uint32_t flags,
                         void* stream);
 
+/* Same with a caller-owned workspace (layout and zero-init contract as for aqlm_b200_matmat_dequant_ws below).  With a
+ * workspace, batch-1 calls on 256-entry-codebook schemes (1x8, 2x8, 4x8, 8x8) use the dot-product-LUT kernel
+ * (tensor-core-built LUT in shared memory, conflict-free 4-byte lookups) instead of per-code vector gathers. */
+size_t aqlm_b200_matmat_workspace_bytes(const aqlm_b200_weight_t* w, int64_t batch);
+int aqlm_b200_matmat_ws(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, uint32_t flags,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused dequant + tensor-core GEMM for large batch: W never goes to HBM.  Replaces
  * code{1x16,2x8,1x8}_matmat_dequant (cuda_kernel.cpp:249-301, 450-484, 615-649: Dequant kernel ->
  * full W in HBM -> cuBLAS F::linear -> epilogue). */

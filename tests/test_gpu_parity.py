@@ -359,3 +359,29 @@ def test_tcgen05_gemm_without_workspace_matches_split():
     _cabi.check(_cabi.lib().aqlm_b200_matmat_dequant(ctypes.byref(w), t["x"].data_ptr(), y.data_ptr(), 32,
                                                      torch.cuda.current_stream().cuda_stream))
     assert O.relative_error(y.float().cpu().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
+
+
+# ---- Kx8 dot-product-LUT GEMV (batch 1) -------------------------------------------------------------------------
+@pytest.mark.parametrize("K", [1, 2, 4, 8])
+@pytest.mark.parametrize("fin,fout", [(4096, 4096), (4096, 11008), (11008, 4096), (1032, 77), (264, 33)])
+def test_lut_gemv_kx8(K, fin, fout):
+    """BASELINE configs[2] shapes (Llama-2-7B) plus ragged sizes (in_groups not a multiple of the 32-group slab)."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    g = torch.Generator(device=DEV).manual_seed(K * 1000 + fin + fout)
+    codes = torch.randint(-128, 128, (fout, fin // 8, K), dtype=torch.int8, device=DEV, generator=g)
+    codebooks = torch.randn((K, 256, 1, 8), dtype=torch.float16, device=DEV, generator=g)
+    scales = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=DEV, generator=g)).half()
+    bias = torch.randn((fout,), dtype=torch.float16, device=DEV, generator=g)
+    x = torch.randn((1, fin), dtype=torch.float16, device=DEV, generator=g)
+    y = cuda_kernel.matmat(x, codes, codebooks, scales, bias).float()
+    ref = _gpu_ref(x, codes, codebooks, scales, bias)
+    # the GPU reference rounds W to fp16 (one extra rounding per weight); compare with the fp32-exact oracle budget
+    rel = ((y - ref).abs().mean() / ref.abs().mean()).item()
+    assert rel < TOL_NORTH_STAR / 2, rel
+    y2 = cuda_kernel.matmat(x, codes, codebooks, scales, bias).float()
+    assert torch.equal(y, y2)  # fixed-order slab reduction
+    if fin * fout <= 1032 * 77:
+        case = dict(x=x.cpu().numpy(), codes=codes.cpu().numpy(), codebooks=codebooks.cpu().numpy(),
+                    scales=scales.cpu().numpy(), bias=bias.cpu().numpy())
+        assert O.relative_error(y.cpu().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
