@@ -59,54 +59,8 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
   const int slab = blockIdx.x, rb = blockIdx.y;
   const int j0 = slab * J;
   griddep_launch_dependents();
-  griddep_wait();  // x is produced by the previous kernel
 
-  // ---------------- LUT build: D[16 entries x 8 groups] = CB[16 x 8] . X^T[8 x 8], tensor cores ----------------
-  {
-    const int q = lane >> 2, m = lane & 3;
-    // B fragments: column n = q of n-tile t  <->  group j0 + (J/4)*(q>>1)... see mapping below; k = 2m, 2m+1
-    // column (2m'+i) of n-tile t holds group  (2*NT)*m' + 2t + i  so that a lane ends up with 2*NT consecutive groups
-    uint32_t bfrag[NT];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      const int g = j0 + (2 * NT) * (q >> 1) + 2 * t + (q & 1);
-      uint32_t v = 0;
-      if (g < p.in_groups) v = reinterpret_cast<const uint32_t*>(p.x)[g * 4 + m];
-      bfrag[t] = v;
-    }
-    const uint32_t* cb32 = reinterpret_cast<const uint32_t*>(p.codebooks);
-    for (int mt = warp; mt < K * 16; mt += kWarps) {  // 16-entry tiles over all K codebooks
-      const int e0 = mt * 16;                          // global entry index (k*256 + c)
-      const uint32_t a0 = cb32[(size_t)(e0 + q) * 4 + m];
-      const uint32_t a1 = cb32[(size_t)(e0 + q + 8) * 4 + m];
-      float d[NT][4];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        d[t][0] = d[t][1] = d[t][2] = d[t][3] = 0.f;
-        mma_m16n8k8(d[t], a0, a1, bfrag[t], DT<T>::is_bf16);
-      }
-      // lane holds, for entry e0+q, groups (2NT)m .. (2NT)m + 2NT-1 in d[t][0..1]; for entry e0+q+8 in d[t][2..3]
-      float* r0 = lut + (size_t)(e0 + q) * J + (2 * NT) * m;
-      float* r1 = lut + (size_t)(e0 + q + 8) * J + (2 * NT) * m;
-      if constexpr (NT == 4) {
-        // two 16-byte stores per entry; odd rows store the upper half first so that a quarter-warp hits 32 distinct banks
-        const bool odd = q & 1;
-        float4 lo0 = make_float4(d[0][0], d[0][1], d[1][0], d[1][1]), hi0 = make_float4(d[2][0], d[2][1], d[3][0], d[3][1]);
-        float4 lo1 = make_float4(d[0][2], d[0][3], d[1][2], d[1][3]), hi1 = make_float4(d[2][2], d[2][3], d[3][2], d[3][3]);
-        *reinterpret_cast<float4*>(r0 + (odd ? 4 : 0)) = odd ? hi0 : lo0;
-        *reinterpret_cast<float4*>(r0 + (odd ? 0 : 4)) = odd ? lo0 : hi0;
-        *reinterpret_cast<float4*>(r1 + (odd ? 4 : 0)) = odd ? hi1 : lo1;
-        *reinterpret_cast<float4*>(r1 + (odd ? 0 : 4)) = odd ? lo1 : hi1;
-      } else {
-        // J = 16: one 16-byte store per entry; consecutive entries alternate bank halves
-        *reinterpret_cast<float4*>(r0) = make_float4(d[0][0], d[0][1], d[1][0], d[1][1]);
-        *reinterpret_cast<float4*>(r1) = make_float4(d[0][2], d[0][3], d[1][2], d[1][3]);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---------------- lookups: lane <-> group, 32/RPW... rows in flight per warp ----------------
+  // lane <-> group mapping of the lookup phase
   const int jj = lane & (J - 1);
   const int rsub = lane / J;  // 0 for J == 32; 0/1 for J == 16
   const int g = j0 + jj;
@@ -116,13 +70,11 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
   const float* lbase = lut + jj;
   const int row_begin = rb * p.rows_per_block;
   const int row_end = min(p.out_features, row_begin + p.rows_per_block);
-  constexpr int RB = J;  // rows per lane-batch (each lane accumulates RB values, the butterfly leaves one row per lane)
+  constexpr int RB = J;  // values per lane per batch; the butterfly leaves one row total per lane
+  constexpr int CWN = (K + 3) / 4;
   float* part = p.ws_partials + (size_t)slab * p.out_features;
 
-  for (int r0 = row_begin + warp * (RB * RPW); r0 < row_end; r0 += kWarps * RB * RPW) {
-    float v[RB];
-    // all code loads of the batch first (RB independent loads in flight per lane)
-    uint32_t cw[RB][(K + 3) / 4];
+  auto load_codes = [&](int r0, uint32_t (&cw)[RB][CWN]) {
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
       const int row = r0 + i * RPW + rsub;
@@ -136,19 +88,84 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
         cw[i][0] = t2.x; cw[i][1] = t2.y;
       }
     }
+  };
+
+  // ---- prologue (weights only, overlaps the previous kernel under PDL): first batch of codes (HBM) and this warp's
+  //      codebook fragments (L2) go in flight before anything waits ----
+  uint32_t cw[RB][CWN];
+  int r0 = row_begin + warp * (RB * RPW);
+  load_codes(r0, cw);
+  constexpr int MT = (K * 16) / kWarps;  // 16-entry tiles per warp (K*16 tiles, 8 warps)
+  static_assert((K * 16) % kWarps == 0, "tiles must divide evenly");
+  const int q = lane >> 2, m = lane & 3;
+  uint32_t afrag[MT][2];
+  {
+    const uint32_t* cb32 = reinterpret_cast<const uint32_t*>(p.codebooks);
+#pragma unroll
+    for (int u = 0; u < MT; ++u) {
+      const int e0 = (warp + u * kWarps) * 16;  // global entry index (k*256 + c)
+      afrag[u][0] = __ldg(cb32 + (size_t)(e0 + q) * 4 + m);
+      afrag[u][1] = __ldg(cb32 + (size_t)(e0 + q + 8) * 4 + m);
+    }
+  }
+  griddep_wait();  // x is produced by the previous kernel
+
+  // ---------------- LUT build: D[16 entries x 8 groups] = CB[16 x 8] . X^T[8 x 8], tensor cores ----------------
+  {
+    // column (2m'+i) of n-tile t holds group (2*NT)*m' + 2t + i, so a lane ends up with 2*NT consecutive groups
+    uint32_t bfrag[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int gg = j0 + (2 * NT) * (q >> 1) + 2 * t + (q & 1);
+      uint32_t v = 0;
+      if (gg < p.in_groups) v = reinterpret_cast<const uint32_t*>(p.x)[gg * 4 + m];
+      bfrag[t] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < MT; ++u) {
+      const int e0 = (warp + u * kWarps) * 16;
+      float d[NT][4];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        d[t][0] = d[t][1] = d[t][2] = d[t][3] = 0.f;
+        mma_m16n8k8(d[t], afrag[u][0], afrag[u][1], bfrag[t], DT<T>::is_bf16);
+      }
+      // lane holds, for entry e0+q, groups (2NT)m .. (2NT)m + 2NT-1 in d[t][0..1]; for entry e0+q+8 in d[t][2..3]
+      float* ra = lut + (size_t)(e0 + q) * J + (2 * NT) * m;
+      float* rb8 = lut + (size_t)(e0 + q + 8) * J + (2 * NT) * m;
+      if constexpr (NT == 4) {
+        // two 16-byte stores per entry; odd rows store the upper half first so that a quarter-warp hits 32 distinct banks
+        const bool odd = q & 1;
+        const float4 lo0 = make_float4(d[0][0], d[0][1], d[1][0], d[1][1]), hi0 = make_float4(d[2][0], d[2][1], d[3][0], d[3][1]);
+        const float4 lo1 = make_float4(d[0][2], d[0][3], d[1][2], d[1][3]), hi1 = make_float4(d[2][2], d[2][3], d[3][2], d[3][3]);
+        *reinterpret_cast<float4*>(ra + (odd ? 4 : 0)) = odd ? hi0 : lo0;
+        *reinterpret_cast<float4*>(ra + (odd ? 0 : 4)) = odd ? lo0 : hi0;
+        *reinterpret_cast<float4*>(rb8 + (odd ? 4 : 0)) = odd ? hi1 : lo1;
+        *reinterpret_cast<float4*>(rb8 + (odd ? 0 : 4)) = odd ? lo1 : hi1;
+      } else {
+        // J = 16: one 16-byte store per entry; consecutive entries alternate bank halves
+        *reinterpret_cast<float4*>(ra) = make_float4(d[0][0], d[0][1], d[1][0], d[1][1]);
+        *reinterpret_cast<float4*>(rb8) = make_float4(d[0][2], d[0][3], d[1][2], d[1][3]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- lookups: lane <-> group <-> bank; codes of the next batch are prefetched ----------------
+  for (; r0 < row_end; r0 += kWarps * RB * RPW) {
+    float v[RB];
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
-      const int row = r0 + i * RPW + rsub;
       float acc = 0.f;
-      if (g_ok && row < row_end) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const uint32_t c = (cw[i][k >> 2] >> ((k & 3) * 8)) & 0xffu;
-          acc += lbase[(size_t)(k * 256 + c) * J];
-        }
+      for (int k = 0; k < K; ++k) {
+        const uint32_t c = (cw[i][k >> 2] >> ((k & 3) * 8)) & 0xffu;
+        acc += lbase[(size_t)(k * 256 + c) * J];  // rows/groups out of range hold code 0: harmless, never stored
       }
       v[i] = acc;
     }
+    const int rnext = r0 + kWarps * RB * RPW;
+    if (rnext < row_end) load_codes(rnext, cw);
     // transpose-reduce over the J lanes of a row group: lane jj ends with the total of row index jj of the batch
 #pragma unroll
     for (int d = J / 2, n = RB; d >= 1; d >>= 1, n >>= 1) {
@@ -178,7 +195,15 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
     __threadfence();
     for (int row = row_begin + tid; row < row_end; row += kLutThreads) {
       float acc = 0.f;
-      for (int s = 0; s < p.n_slabs; ++s) acc += __ldcg(p.ws_partials + (size_t)s * p.out_features + row);
+      int s = 0;
+      for (; s + 8 <= p.n_slabs; s += 8) {  // 8 independent L2 loads in flight, added in slab order
+        float t8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t8[u] = __ldcg(p.ws_partials + (size_t)(s + u) * p.out_features + row);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += t8[u];
+      }
+      for (; s < p.n_slabs; ++s) acc += __ldcg(p.ws_partials + (size_t)s * p.out_features + row);
       if (p.partial_f32) {
         reinterpret_cast<float*>(p.y)[row] = acc;
       } else {
