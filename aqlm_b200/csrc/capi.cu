@@ -243,10 +243,11 @@ static LutPlan lut_plan(const aqlm_b200_weight_t* w, int64_t batch, const Device
   L.smem = (size_t)K * 256 * L.J * 4;
   if (L.smem + 1024 > (size_t)di->max_smem_optin) return L;
   int per_sm = (int)((size_t)di->max_smem_optin / (L.smem + 1024));
-  const int want = env_int("AQLM_B200_LUT_CTAS_PER_SM", 2);
+  const int want = env_int("AQLM_B200_LUT_CTAS_PER_SM", 2);  // 128 regs x 256 threads: registers allow 2
   if (per_sm > want) per_sm = want;
   if (per_sm < 1) per_sm = 1;
-  int rb = (di->sm_count * per_sm + L.n_slabs - 1) / L.n_slabs;
+  // the whole grid must be resident at once (ONE wave): a few CTAs spilling into a second wave double the time
+  int rb = (di->sm_count * per_sm) / L.n_slabs;
   if (rb < 1) rb = 1;
   int rpb = (int)((w->out_features + rb - 1) / rb);
   rpb = (rpb + 31) / 32 * 32;
@@ -275,7 +276,8 @@ static int launch_lut(const aqlm_b200_weight_t* w, const void* input, void* outp
   p.n_slabs = L.n_slabs;
   p.rows_per_block = L.rows_per_block;
   p.partial_f32 = (flags & AQLM_B200_FLAG_PARTIAL_F32) ? 1 : 0;
-  auto kernel = gemv_lut_kernel<T, K, J>;
+  constexpr int THREADS = (K <= 2) ? 256 : 512;  // K >= 4: one CTA per SM (128 KiB LUT), so give it 16 warps
+  auto kernel = gemv_lut_kernel<T, K, J, THREADS>;
   static std::atomic<size_t> configured{0};
   if (configured.load(std::memory_order_relaxed) < L.smem) {
     int rc = set_smem(kernel, L.smem);
@@ -284,7 +286,7 @@ static int launch_lut(const aqlm_b200_weight_t* w, const void* input, void* outp
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(L.n_slabs, L.row_blocks);
-  cfg.blockDim = dim3(kLutThreads);
+  cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -352,7 +354,9 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
     g.n_tiles = (int)((batch + 255) / 256);
   }
   const size_t budget = (size_t)di->max_smem_optin;
-  int S = 6;
+  // At most 3 stages: shared memory taken here is L1 taken from the codebook gathers (outstanding misses need L1
+  // lines); measured at N=256: 4 stages 335 TFLOP/s, 3 stages 484-503, 2 stages 470 (profiles/r01/gemm_experiments.md)
+  int S = 3;
   while (S > 2 && gemm_smem_layout(S, g.n_tile).total > budget) --S;
   if (gemm_smem_layout(S, g.n_tile).total > budget) return g;
   const int forced_s = env_int("AQLM_B200_GEMM_STAGES", 0);
@@ -441,6 +445,7 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   p.stages = g.stages;
   p.cluster = g.cluster;
   p.debug = env_int("AQLM_B200_GEMM_DEBUG", 0);
+  p.gather_mode = env_int("AQLM_B200_GEMM_GATHER_MODE", 1);  // ld.global.cg: do not allocate gather lines in the small L1
   p.codes = w->codes;
   p.row_bytes = (long long)(w->in_features / 8) * K * CB;
   const size_t smem = gemm_smem_layout(g.stages, g.n_tile).total;

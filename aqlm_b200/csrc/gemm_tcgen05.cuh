@@ -44,6 +44,7 @@ struct GemmParams {
   int n_tile;           // N of the MMA (multiple of 16, <= 256)
   int stages;
   int cluster;          // CTAs per cluster along M that share (multicast) the X tiles
+  int gather_mode;      // 0: ld.global.nc (L1 allocate), 1: ld.global.cg, 3: nc.L1::no_allocate
   int debug;            // bit0: read codes from global instead of the TMA code tile; bit1: no producer run-ahead
   const void* codes;    // (debug bit0)
   long long row_bytes;  // (debug bit0)
@@ -219,10 +220,13 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S, it = i / S;
         if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
-        mbar_expect_tx(full_bar(s), (uint32_t)N * 128);  // all C slices land here
-        if (C == 1) {
+        if (p.debug & 4) {  // experiment: no X traffic (B tile keeps whatever it holds)
+          mbar_arrive(full_bar(s));
+        } else if (C == 1) {
+          mbar_expect_tx(full_bar(s), (uint32_t)N * 128);
           tma_load_2d(base + L.b + s * N * 128, &tmap_x, (kb0 + i) * kGemmBlockK, n0, full_bar(s));
         } else {
+          mbar_expect_tx(full_bar(s), (uint32_t)N * 128);  // all C slices land here
           // this CTA fetches rows [crank*N/C, (crank+1)*N/C) of the X tile and multicasts them to the whole cluster;
           // empty_bar(s) (count C) guarantees every CTA of the cluster has released stage s
           const int rows = N / C;
@@ -259,7 +263,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
       constexpr int CB2 = 2 * K * CODE_BYTES;  // code bytes of this thread's 2 groups
       constexpr int CW = (CB2 + 3) / 4;        // 32-bit words holding them
-      constexpr bool PIPE = (K <= 2);          // double-buffer the gathered vectors when registers allow
+      constexpr int D = (K == 1) ? 4 : (K == 2 ? 2 : 1);  // k-blocks of gathers held in registers ahead of the writes
 
       // codes of k-block index i (relative) -> issue the 2*K gathers into wv
       auto issue = [&](int i, uint4 (&wv)[2][K]) {
@@ -303,7 +307,11 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             uint32_t code;
             if constexpr (CODE_BYTES == 2) code = (cw[idx >> 1] >> ((idx & 1) * 16)) & 0xffffu;
             else code = (cw[idx >> 2] >> ((idx & 3) * 8)) & 0xffu;
-            wv[e][k] = ld_gather_v4<0>(gcb + (((size_t)k << p.nbits) + code));
+            const uint4* gp = gcb + (((size_t)k << p.nbits) + code);
+            if (p.debug & 8) wv[e][k] = make_uint4(code, code, code, code);  // experiment: no gathers
+            else if (p.gather_mode == 1) wv[e][k] = ld_gather_v4<1>(gp);       // ld.global.cg (L2 only)
+            else if (p.gather_mode == 3) wv[e][k] = ld_gather_v4<3>(gp);       // nc + L1::no_allocate
+            else wv[e][k] = ld_gather_v4<0>(gp);
           }
         }
         // Release the code tile after its last k-block.  This MUST come after the gathers above were issued: their
@@ -337,22 +345,19 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(s));
       };
-      if constexpr (PIPE) {
-        uint4 w0[2][K], w1[2][K];
-        issue(0, w0);
-        for (int i = 0; i < nkb; i += 2) {
-          if (i + 1 < nkb) issue(i + 1, w1);
-          commit(i, w0);
-          if (i + 1 < nkb) {
-            if (i + 2 < nkb) issue(i + 2, w0);
-            commit(i + 1, w1);
+      // register ring of D k-blocks: the kernel is bound by gather LATENCY unless ~8+ gathers per thread are in flight
+      // (ncu: long-scoreboard stalls dominate, L2/XBAR < 30% busy), so gathers run D k-blocks ahead of the smem writes.
+      uint4 w[D][2][K];
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        if (d < nkb) issue(d, w[d]);
+      for (int i = 0; i < nkb; i += D) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          if (i + d < nkb) {
+            commit(i + d, w[d]);
+            if (i + d + D < nkb) issue(i + d + D, w[d]);
           }
-        }
-      } else {
-        uint4 w0[2][K];
-        for (int i = 0; i < nkb; ++i) {
-          issue(i, w0);
-          commit(i, w0);
         }
       }
     }

@@ -36,7 +36,6 @@ struct LutParams {
   int partial_f32;
 };
 
-constexpr int kLutThreads = 256;
 
 __device__ __forceinline__ void mma_m16n8k8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0, bool bf16) {
   if (bf16) {
@@ -49,7 +48,7 @@ __device__ __forceinline__ void mma_m16n8k8(float (&d)[4], uint32_t a0, uint32_t
 }
 
 // K codebooks, J groups per slab (32 -> one row per warp step, 16 -> two rows per warp step)
-template <typename T, int K, int J>
+template <typename T, int K, int J, int kLutThreads>
 __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p) {
   extern __shared__ __align__(16) float lut[];  // [K][256][J]
   constexpr int NT = J / 8;                     // n-tiles (8 groups each) per slab
@@ -92,9 +91,11 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
 
   // ---- prologue (weights only, overlaps the previous kernel under PDL): first batch of codes (HBM) and this warp's
   //      codebook fragments (L2) go in flight before anything waits ----
-  uint32_t cw[RB][CWN];
+  constexpr int kBatchStride = kWarps * RB * RPW;
+  uint32_t cwa[RB][CWN], cwb[RB][CWN];
   int r0 = row_begin + warp * (RB * RPW);
-  load_codes(r0, cw);
+  load_codes(r0, cwa);
+  if (r0 + kBatchStride < row_end) load_codes(r0 + kBatchStride, cwb);
   constexpr int MT = (K * 16) / kWarps;  // 16-entry tiles per warp (K*16 tiles, 8 warps)
   static_assert((K * 16) % kWarps == 0, "tiles must divide evenly");
   const int q = lane >> 2, m = lane & 3;
@@ -151,8 +152,8 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
   }
   __syncthreads();
 
-  // ---------------- lookups: lane <-> group <-> bank; codes of the next batch are prefetched ----------------
-  for (; r0 < row_end; r0 += kWarps * RB * RPW) {
+  // ---------------- lookups: lane <-> group <-> bank; two batches of code loads are always in flight ----------------
+  auto process = [&](int rbase, uint32_t (&cw)[RB][CWN]) {
     float v[RB];
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
       }
       v[i] = acc;
     }
-    const int rnext = r0 + kWarps * RB * RPW;
-    if (rnext < row_end) load_codes(rnext, cw);
+    // refill this buffer with the batch after next before the shuffle phase
+    if (rbase + 2 * kBatchStride < row_end) load_codes(rbase + 2 * kBatchStride, cw);
     // transpose-reduce over the J lanes of a row group: lane jj ends with the total of row index jj of the batch
 #pragma unroll
     for (int d = J / 2, n = RB; d >= 1; d >>= 1, n >>= 1) {
@@ -177,8 +178,12 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
       }
     }
-    const int row = r0 + jj * RPW + rsub;
+    const int row = rbase + jj * RPW + rsub;
     if (row < row_end) part[row] = v[0];
+  };
+  for (; r0 < row_end; r0 += 2 * kBatchStride) {
+    process(r0, cwa);
+    if (r0 + kBatchStride < row_end) process(r0 + kBatchStride, cwb);
   }
 
   // ---------------- fix-up: the last slab CTA of this row block adds the slabs in order ----------------

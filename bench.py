@@ -216,6 +216,73 @@ def build_model(model, K, nbits, n_layers, device, rank, world):
     return layers
 
 
+def secondary_metrics(device, peak_hbm):
+    """Short extra measurements reported beside the headline (not part of `value`): the batch-256 fused dequant+tcgen05
+    GEMM (BASELINE configs[3]) and the Kx8 LUT matvec (configs[2]).  CUDA-graph replay over rotating weight copies."""
+    import torch
+
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            tpeak = float(json.load(f)["bf16_tflops"])
+    except Exception:
+        tpeak = 1590.0
+
+    def timed(fns, iters=10):
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for f in fns:
+                f()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / iters / len(fns)  # us per call
+
+    def weights(fin, fout, K, nbits, copies, dt):
+        ws = []
+        for _ in range(copies):
+            lo, hi = (-128, 128) if nbits <= 8 else (-32768, 32768)
+            codes = torch.randint(lo, hi, (fout, fin // 8, K), dtype=torch.int8 if nbits <= 8 else torch.int16, device=device)
+            cb = torch.randn((K, 2**nbits, 1, 8), dtype=dt, device=device)
+            sc = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=device)).to(dt)
+            ws.append((codes, cb, sc))
+        return ws
+
+    out = {"gemm": [], "kx8_matvec": []}
+    fin, fout = 4096, 14336
+    for dt, name in ((torch.float16, "f16"), (torch.bfloat16, "bf16")):
+        ws = weights(fin, fout, 1, 16, 12, dt)
+        for bs in (16, 64, 256):
+            x = torch.randn((bs, fin), dtype=dt, device=device)
+            us = timed([(lambda w=w: cuda_kernel.matmat_dequant(x, w[0], w[1], w[2], None)) for w in ws])
+            tf = 2.0 * bs * fin * fout / us / 1e6
+            out["gemm"].append({"shape": f"{fin}x{fout}", "scheme": "1x16", "batch": bs, "operands": name, "us": round(us, 2),
+                                "tflops": round(tf, 1), "frac_of_measured_bf16_peak": round(tf / tpeak, 4)})
+        del ws
+    for K, nbits, shape in ((2, 8, (4096, 11008)), (8, 8, (4096, 11008)), (2, 8, (4096, 4096))):
+        fin, fout = shape
+        cb = fout * (fin // 8) * K
+        ws = weights(fin, fout, K, nbits, max(2, min(40, 300 * 2**20 // cb)), torch.float16)
+        x = torch.randn((1, fin), dtype=torch.float16, device=device)
+        us = timed([(lambda w=w: cuda_kernel.matmat(x, w[0], w[1], w[2], None)) for w in ws])
+        out["kx8_matvec"].append({"shape": f"{fin}x{fout}", "scheme": f"{K}x{nbits}", "us": round(us, 2),
+                                  "code_GBps": round(cb / us / 1e3, 1), "frac_of_hbm_peak": round(cb / us / 1e3 / peak_hbm, 4)})
+        del ws
+    out["tensor_peak_tflops"] = tpeak
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -384,6 +451,13 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
         }
+        if world == 1 and not args.skip_secondary:
+            try:
+                del layers, graph
+                torch.cuda.empty_cache()
+                line["secondary"] = secondary_metrics(device, peak)
+            except Exception as e:  # never lose the headline line to a secondary measurement
+                line["secondary"] = {"error": f"{type(e).__name__}: {e}"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if same_n1 is not None:
@@ -405,6 +479,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-n1", action="store_true")
+    ap.add_argument("--skip-secondary", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
