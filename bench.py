@@ -464,7 +464,18 @@ def run_ours(args):
             line["same_workload_single_gpu"] = same_n1
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down without touching the NCCL communicator: destroying it while CUDA graphs that captured NCCL kernels
+        # are alive hung for the watchdog's full timeout on this stack (profiles/r01/README.md).  Everything is already
+        # synchronised and printed; leave through os._exit so no destructor runs.
+        try:
+            del graph
+        except Exception:
+            pass
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
