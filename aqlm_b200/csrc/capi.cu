@@ -121,6 +121,32 @@ static int launch_vec(const GemvParams& p, const DeviceInfo* di, cudaStream_t st
   return AQLM_B200_OK;
 }
 
+template <typename T, int BT, int GM>
+static int launch_1x16(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
+  const int grid = di->sm_count;
+  const size_t smem = vec_smem_bytes(p, 1, 2, 8, BT, false, grid);
+  auto kernel = gemv_1x16_kernel<T, BT, GM>;
+  static std::atomic<size_t> configured{0};
+  if (configured.load(std::memory_order_relaxed) < smem) {
+    int rc = set_smem(kernel, smem);
+    if (rc) return rc;
+    configured.store(smem, std::memory_order_relaxed);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemv1x16Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = env_int("AQLM_B200_PDL", 1) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
+  count_launch();
+  return AQLM_B200_OK;
+}
+
 template <typename T, int CB, int G, int BT>
 static int launch_generic(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
   int blocks = (p.out_features + 7) / 8;
@@ -144,6 +170,10 @@ static int dispatch_bt(const aqlm_b200_weight_t* w, const GemvParams& p, const D
   const size_t need = pow2k ? vec_smem_bytes(p, K, code_bytes, G, BT, nbits == 8, grid) : (size_t)-1;
   if (vec_ok && nbits == 16 && K == 1 && need <= budget) {
     const int gm = env_int("AQLM_B200_GATHER_MODE", 0);
+    if (G == 8 && env_int("AQLM_B200_GEMV_V2", 1) && vec_smem_bytes(p, 1, 2, 8, BT, false, di->sm_count) <= budget) {
+      if (gm == 1) return launch_1x16<T, BT, 1>(p, di, st);
+      return launch_1x16<T, BT, 0>(p, di, st);
+    }
     if (G == 8) {
       if (gm == 1) return launch_vec<T, 1, 2, 8, BT, false, 1>(p, di, st);
       if (gm == 2) return launch_vec<T, 1, 2, 8, BT, false, 2>(p, di, st);

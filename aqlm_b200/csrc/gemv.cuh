@@ -190,6 +190,120 @@ __global__ void __launch_bounds__(THREADS, 1) gemv_vec_kernel(const GemvParams p
 }
 
 // ---------------------------------------------------------------------------------------------------
+// 1x16 (g = 8) specialisation of the vector path: same decomposition and reduction as gemv_vec_kernel, but
+//   * 512-thread CTAs (<= 128 registers): a PDL-launched successor kernel can be co-resident on the SM, so its
+//     weight-only prologue (code loads AND the first codebook gathers) overlaps this kernel's tail;
+//   * two tasks per warp in flight (double-buffered gather registers): 16 gathers per lane outstanding.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kGemv1x16Threads = 512;
+
+template <typename T, int BT, int GM>
+__global__ void __launch_bounds__(kGemv1x16Threads, 1) gemv_1x16_kernel(const GemvParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int THREADS = kGemv1x16Threads;
+  constexpr int kWarps = THREADS / 32;
+  const int upr = p.in_features >> 3;
+  griddep_launch_dependents();
+  if ((int)blockIdx.x >= p.out_features) return;
+
+  uint4* sx = reinterpret_cast<uint4*>(smem_raw);
+  float* spart = reinterpret_cast<float*>(sx + BT * upr);  // [rows_cta][slices][BT]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunks = p.in_groups >> 3;
+  const int slices = (chunks + kSliceChunks - 1) / kSliceChunks;
+  const int rows_cta = (p.out_features - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tasks = rows_cta * slices;
+  const size_t row_bytes = (size_t)p.in_groups * 2;
+  const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
+
+  auto load_codes = [&](int t, bool& live) -> uint4 {
+    const int ri = t / slices;
+    const int c = (t - ri * slices) * kSliceChunks + lane;
+    live = (t < tasks) && (c < chunks);
+    if (!live) return make_uint4(0, 0, 0, 0);
+    const int row = (int)blockIdx.x + ri * (int)gridDim.x;
+    return ld_stream_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.codes) + row * row_bytes) + c);
+  };
+  auto gather = [&](const uint4& cw, uint4 (&w)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = ld_gather_v4<GM>(gcb + chunk_code<2>(cw, e));
+  };
+  auto consume = [&](int t, bool live, const uint4 (&w)[8]) {
+    float acc[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+    if (live) {
+      const int c = (t % slices) * kSliceChunks + lane;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[b] = dot8<T>(w[e], sx[b * upr + swz16(c * 8 + e)], acc[b]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = warp_sum(acc[b]);
+    if (lane == 0) {
+#pragma unroll
+      for (int b = 0; b < BT; ++b) spart[(size_t)t * BT + b] = acc[b];
+    }
+  };
+
+  // ---- weight-only prologue (may overlap the previous kernel under PDL) ----
+  bool liveA = false, liveB = false;
+  uint4 wA[8], wB[8];
+  uint4 cwA = load_codes(warp, liveA);
+  uint4 cwB = load_codes(warp + kWarps, liveB);
+  if (liveA) gather(cwA, wA);
+  griddep_wait();
+  {
+    const uint4* gx = reinterpret_cast<const uint4*>(p.x);
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      if (b < p.batch) {
+        for (int u = tid; u < upr; u += THREADS) sx[b * upr + swz16(u)] = gx[(size_t)b * upr + u];
+      } else {
+        for (int u = tid; u < upr; u += THREADS) sx[b * upr + u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  __syncthreads();
+
+  for (int t = warp; t < tasks; t += 2 * kWarps) {
+    // A = task t (gathers already in flight), B = task t + kWarps (codes loaded)
+    if (liveB) gather(cwB, wB);
+    bool liveA2;
+    cwA = load_codes(t + 2 * kWarps, liveA2);
+    consume(t, liveA, wA);
+    liveA = liveA2;
+    if (liveA) gather(cwA, wA);
+    const int tb = t + kWarps;
+    bool liveB2;
+    const bool haveB = tb < tasks;
+    const bool liveBcur = liveB;
+    cwB = load_codes(t + 3 * kWarps, liveB2);
+    if (haveB) consume(tb, liveBcur, wB);
+    liveB = liveB2;
+  }
+  __syncthreads();
+
+  for (int i = tid; i < rows_cta * BT; i += THREADS) {
+    const int ri = i / BT;
+    const int b = i - ri * BT;
+    if (b >= p.batch) continue;
+    const int row = (int)blockIdx.x + ri * (int)gridDim.x;
+    float v = 0.f;
+    for (int sl = 0; sl < slices; ++sl) v += spart[((size_t)ri * slices + sl) * BT + b];
+    if (p.partial_f32) {
+      reinterpret_cast<float*>(p.y)[(size_t)b * p.out_features + row] = v;
+    } else {
+      const float s = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+      const float bv = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
+      reinterpret_cast<T*>(p.y)[(size_t)b * p.out_features + row] = DT<T>::from_float(fmaf(v, s, bv));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Generic path: any K <= 16, any nbits <= 16, ragged rows (row bytes not a multiple of 16).  One group
 // per lane per step, scalar code loads, x read through L1.  Slow but complete (the reference falls
 // back to Triton / embedding_bag here, kernel_selector.py:91-102).
