@@ -86,6 +86,15 @@ def lib():
                 L.aqlm_b200_matmat_dequant_transposed.argtypes = [wp, vp, vp, i64, vp, vp]
                 L.aqlm_b200_scale_bias.argtypes = [vp, vp, vp, vp, i64, i64, i32, vp]
                 L.aqlm_b200_matmat_host.argtypes = [wp, vp, vp, vp, vp, i64, vp]
+                L.aqlm_b200_comm_shared_bytes.argtypes = [ctypes.c_int, i64]
+                L.aqlm_b200_comm_shared_bytes.restype = ctypes.c_size_t
+                L.aqlm_b200_shared_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp), vp]
+                L.aqlm_b200_shared_open.argtypes = [vp, ctypes.POINTER(vp)]
+                L.aqlm_b200_comm_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), i64, ctypes.POINTER(vp)]
+                L.aqlm_b200_comm_partials.argtypes = [vp]
+                L.aqlm_b200_comm_partials.restype = vp
+                L.aqlm_b200_comm_destroy.argtypes = [vp]
+                L.aqlm_b200_allreduce_scale_bias.argtypes = [vp, vp, vp, vp, vp, i64, i64, i32, vp]
                 flat_mm_g = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp]
                 flat_mm = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, vp]
                 L.aqlm_b200_code1x16_matmat.argtypes = flat_mm_g

@@ -10,6 +10,7 @@
 #include "gemm_tcgen05.cuh"
 #include "gemv.cuh"
 #include "gemv_lut.cuh"
+#include "peer_allreduce.cuh"
 
 namespace aqlm_b200 {
 
@@ -659,6 +660,106 @@ int aqlm_b200_scale_bias(const float* partial, const void* scales, const void* b
                                                              out_features);
   count_launch();
   AQLM_CUDA_CHECK(cudaGetLastError());
+  return AQLM_B200_OK;
+}
+
+// ---- peer-memory all-reduce (multi-GPU sharded path) -----------------------------------------------
+struct aqlm_b200_comm {
+  int rank, world;
+  long long max_elems;
+  uint8_t* peer_base[kPeerMaxWorld];
+  unsigned int* local_state;  // [0] step, [1..2] tickets
+  float* local_partials;      // [max_elems]
+};
+
+size_t aqlm_b200_comm_shared_bytes(int world, int64_t max_elems) {
+  if (world < 1 || world > kPeerMaxWorld || max_elems <= 0) return 0;
+  return (size_t)kPeerFlagBytes + (size_t)2 * world * (size_t)max_elems * sizeof(float);
+}
+
+int aqlm_b200_shared_alloc(size_t bytes, void** ptr, void* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return fail(AQLM_B200_ERR_SHAPE, "bad shared_alloc arguments");
+  AQLM_CUDA_CHECK(cudaMalloc(ptr, bytes));
+  AQLM_CUDA_CHECK(cudaMemset(*ptr, 0, bytes));
+  AQLM_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  AQLM_CUDA_CHECK(cudaIpcGetMemHandle(&h, *ptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return AQLM_B200_OK;
+}
+
+int aqlm_b200_shared_open(const void* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail(AQLM_B200_ERR_SHAPE, "bad shared_open arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  AQLM_CUDA_CHECK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return AQLM_B200_OK;
+}
+
+int aqlm_b200_comm_create(int rank, int world, void* const* peer_ptrs, int64_t max_elems, aqlm_b200_comm** out) {
+  if (!out || !peer_ptrs || world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world || max_elems <= 0 || (max_elems & 3))
+    return fail(AQLM_B200_ERR_SHAPE, "bad comm_create arguments");
+  aqlm_b200_comm* c = new aqlm_b200_comm();
+  c->rank = rank;
+  c->world = world;
+  c->max_elems = max_elems;
+  for (int r = 0; r < world; ++r) c->peer_base[r] = reinterpret_cast<uint8_t*>(peer_ptrs[r]);
+  AQLM_CUDA_CHECK(cudaMalloc(&c->local_state, 64));
+  AQLM_CUDA_CHECK(cudaMemset(c->local_state, 0, 64));
+  AQLM_CUDA_CHECK(cudaMalloc(&c->local_partials, (size_t)max_elems * sizeof(float)));
+  AQLM_CUDA_CHECK(cudaDeviceSynchronize());
+  *out = c;
+  return AQLM_B200_OK;
+}
+
+void* aqlm_b200_comm_partials(aqlm_b200_comm* c) { return c ? c->local_partials : nullptr; }
+
+int aqlm_b200_comm_destroy(aqlm_b200_comm* c) {
+  if (!c) return AQLM_B200_OK;
+  cudaFree(c->local_state);
+  cudaFree(c->local_partials);
+  delete c;
+  return AQLM_B200_OK;
+}
+
+int aqlm_b200_allreduce_scale_bias(aqlm_b200_comm* c, const float* partial, const void* scales, const void* bias,
+                                   void* output, int64_t batch, int64_t out_features, int32_t dtype, void* stream) {
+  if (!c || !partial || !scales || !output) return fail(AQLM_B200_ERR_SHAPE, "NULL pointer");
+  if (dtype != AQLM_B200_F16 && dtype != AQLM_B200_BF16) return fail(AQLM_B200_ERR_DTYPE, "dtype must be f16/bf16");
+  const int64_t n = batch * out_features;
+  if (n <= 0) return AQLM_B200_OK;
+  if (n > c->max_elems || (out_features & 3)) return fail(AQLM_B200_ERR_SHAPE, "allreduce: %lld elements exceed the communicator's %lld (or out_features %% 4 != 0)", (long long)n, c->max_elems);
+  const DeviceInfo* di = device_info();
+  if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
+  PeerParams p;
+  for (int r = 0; r < kPeerMaxWorld; ++r) p.peer_base[r] = r < c->world ? c->peer_base[r] : nullptr;
+  p.local = partial;
+  p.scales = scales;
+  p.bias = bias;
+  p.y = output;
+  p.step = c->local_state;
+  p.tickets = c->local_state + 1;
+  p.max_elems = c->max_elems;
+  p.n = (int)n;
+  p.out_features = (int)out_features;
+  p.rank = c->rank;
+  p.world = c->world;
+  int grid = (int)((n / 4 + kPeerThreads - 1) / kPeerThreads);
+  if (grid > 16) grid = 16;  // all CTAs must be co-resident (they wait on each other through the tickets and flags)
+  if (grid < 1) grid = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kPeerThreads);
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = env_int("AQLM_B200_PDL", 1) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (dtype == AQLM_B200_F16) AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, peer_allreduce_epilogue_kernel<__half>, p));
+  else AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, peer_allreduce_epilogue_kernel<__nv_bfloat16>, p));
+  count_launch();
   return AQLM_B200_OK;
 }
 

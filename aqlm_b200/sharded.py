@@ -39,7 +39,7 @@ class ShardedQuantizedLinear(nn.Module):
     def __init__(self, in_features: int, out_features: int, in_group_size: int, out_group_size: int,
                  num_codebooks: int, nbits_per_codebook: int, bias: bool = True, process_group=None,
                  rank: Optional[int] = None, world_size: Optional[int] = None, device=None, dtype=None,
-                 partial_fn: Optional[Callable] = None, epilogue_fn: Optional[Callable] = None):
+                 partial_fn: Optional[Callable] = None, epilogue_fn: Optional[Callable] = None, peer_comm=None):
         super().__init__()
         self.process_group = process_group
         self.rank = dist.get_rank(process_group) if rank is None else rank
@@ -63,6 +63,8 @@ class ShardedQuantizedLinear(nn.Module):
             self.register_parameter("bias", None)
         self._partial_fn = partial_fn
         self._epilogue_fn = epilogue_fn
+        # optional aqlm_b200.peer.PeerComm: the all-reduce + epilogue then run as ONE kernel over NVLink peer memory
+        self.peer_comm = peer_comm
 
     @classmethod
     def from_full(cls, codes, codebooks, scales, bias, process_group=None, rank=None, world_size=None, **kw):
@@ -96,6 +98,9 @@ class ShardedQuantizedLinear(nn.Module):
             raise ValueError(f"input has {input.shape[-1]} features; expected {self.in_features} or {local}")
         flat = input.reshape(-1, local)
         partial = partial_fn(flat, self.codes, self.codebooks)  # [batch, out] fp32, unscaled
+        if self.world_size > 1 and self.peer_comm is not None:
+            out = self.peer_comm.allreduce_scale_bias(partial, self.scales, self.bias, input.dtype)  # the ONE exchange
+            return out.reshape(input.shape[:-1] + (self.out_features,))
         if self.world_size > 1:
             dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.process_group)  # the ONE collective
         out = epilogue_fn(partial, self.scales, self.bias, input.dtype)

@@ -187,7 +187,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------------------
-def build_model(model, K, nbits, n_layers, device, rank, world):
+def build_model(model, K, nbits, n_layers, device, rank, world, peer_comm=None):
     """Random-init modules of the named architecture's linears (no checkpoints offline): per layer a list of
     (module, in_features_local)."""
     import torch
@@ -206,7 +206,7 @@ def build_model(model, K, nbits, n_layers, device, rank, world):
                 local_groups = fin // 8
             else:
                 m = ShardedQuantizedLinear(fin, fout, 8, 1, K, nbits, bias=False, rank=rank, world_size=world,
-                                           device=device, dtype=torch.float16)
+                                           device=device, dtype=torch.float16, peer_comm=peer_comm)
                 local_groups = fin // 8 // world
             m.codes.data = torch.randint(lo, hi, (fout, local_groups, K), dtype=m.codes.dtype, device=device, generator=gen)
             m.codebooks.data = torch.randn((K, 2**nbits, 1, 8), dtype=torch.float16, device=device, generator=gen)
@@ -304,7 +304,19 @@ def run_ours(args):
     total_bytes = model_code_bytes(model, K, nbits, n_layers)
     peak, peak_src = measured_peaks()
 
-    layers = build_model(model, K, nbits, n_layers, device, rank, world)
+    peer_comm, reduce_kind = None, "none"
+    if world > 1:
+        reduce_kind = "nccl all-reduce + epilogue kernel"
+        if os.environ.get("AQLM_B200_ALLREDUCE", "peer") == "peer":
+            try:
+                from aqlm_b200.peer import PeerComm
+
+                peer_comm = PeerComm(max_elems=MODELS[model]["inter"] * 4)
+                reduce_kind = "fused peer-memory exchange + epilogue kernel (NVLink P2P stores, csrc/peer_allreduce.cuh)"
+            except Exception as e:
+                print(f"[bench] peer-memory communicator unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+                peer_comm = None
+    layers = build_model(model, K, nbits, n_layers, device, rank, world, peer_comm)
     in_sizes = sorted({n for mods in layers for _, n in mods})
     x_dev = {n: torch.randn((1, n), dtype=torch.float16, device=device) for n in in_sizes}
     x_host = {n: torch.randn((1, n), dtype=torch.float16).pin_memory() for n in in_sizes}
@@ -438,7 +450,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "tok_s_linears_only": 1e3 / ms_step,
             "config": {"workload": f"{model} {K}x{nbits} g8 all-linear matvec sweep, bs=1, {n_layers} layers x 7 linears",
-                       "parallelism": "single GPU" if world == 1 else f"in_features-sharded x{world}, 1 NCCL all-reduce per linear",
+                       "parallelism": "single GPU" if world == 1 else f"in_features-sharded x{world}, one exchange per linear: {reduce_kind}",
                        "l2_policy": f"inputs larger than L2: {total_bytes / world / 2**20:.0f} MiB of distinct codes per GPU per step",
                        "cuda_graph": bool(use_graph), "code_bytes_per_step": total_bytes},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -111,6 +111,24 @@ int aqlm_b200_matmat_dequant_transposed(const aqlm_b200_weight_t* w, const void*
 int aqlm_b200_scale_bias(const float* partial, const void* scales, const void* bias, void* output, int64_t batch,
                          int64_t out_features, int32_t dtype, void* stream);
 
+/* ---- multi-GPU: one-shot all-reduce over NVLink peer memory, fused with the epilogue ------------------------
+ * One process per GPU.  Each rank allocates a shared buffer of aqlm_b200_comm_shared_bytes() with
+ * aqlm_b200_shared_alloc (cudaMalloc + cudaIpcGetMemHandle; the 64-byte handle is exchanged out of band, e.g. with
+ * torch.distributed.all_gather_object), opens every peer's handle with aqlm_b200_shared_open, and builds a communicator
+ * from the W mapped pointers (peer_ptrs[rank] = its own buffer).  aqlm_b200_allreduce_scale_bias then does, in ONE
+ * kernel: push my fp32 partials into every peer's buffer (P2P stores), publish a release flag, wait for all W flags,
+ * add the W partials in rank order, apply scale + bias, write `output`.  Every rank must call it the same number of
+ * times in the same order.  max_elems bounds batch*out_features of any call. */
+typedef struct aqlm_b200_comm aqlm_b200_comm;
+size_t aqlm_b200_comm_shared_bytes(int world, int64_t max_elems);
+int aqlm_b200_shared_alloc(size_t bytes, void** ptr, void* handle64);
+int aqlm_b200_shared_open(const void* handle64, void** ptr);
+int aqlm_b200_comm_create(int rank, int world, void* const* peer_ptrs, int64_t max_elems, aqlm_b200_comm** out);
+void* aqlm_b200_comm_partials(aqlm_b200_comm* comm); /* a device buffer of max_elems floats owned by the communicator */
+int aqlm_b200_comm_destroy(aqlm_b200_comm* comm);
+int aqlm_b200_allreduce_scale_bias(aqlm_b200_comm* comm, const float* partial, const void* scales, const void* bias,
+                                   void* output, int64_t batch, int64_t out_features, int32_t dtype, void* stream);
+
 /* End-to-end variant with HOST buffers (pinned): H2D copy of `input_host` into `input_dev`, the fused
  * matmat, D2H copy of the result into `output_host`, and a stream synchronize.  `input_dev`/`output_dev`
  * are caller-owned device scratch of batch*in_features / batch*out_features elements. */
