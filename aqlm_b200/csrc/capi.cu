@@ -746,7 +746,7 @@ int aqlm_b200_allreduce_scale_bias(aqlm_b200_comm* c, const float* partial, cons
   p.rank = c->rank;
   p.world = c->world;
   int grid = (int)((n / 4 + kPeerThreads - 1) / kPeerThreads);
-  if (grid > 16) grid = 16;  // all CTAs must be co-resident (they wait on each other through the tickets and flags)
+  if (grid > kPeerMaxCtas) grid = kPeerMaxCtas;  // one flag per (source rank, CTA slice); every rank derives the same grid from n
   if (grid < 1) grid = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

@@ -4,8 +4,8 @@
 // partial output vector per linear; at 32-112 KiB that collective is pure latency (NCCL: ~10-20 us, several times the
 // shard's compute).  Here every rank owns a buffer that all peers have mapped (cudaIpc): in ONE kernel a rank
 //   A. pushes its partial vector into slot [set][my_rank] of every peer's buffer with 16-byte P2P stores,
-//   B. (last CTA) publishes flag[my_rank] = step on every peer with a system-scope release,
-//   C. waits until all W flags in its OWN buffer reach `step` (system-scope acquire),
+//   B. publishes flag[my_rank][slice] = step on every peer with a system-scope release store (per CTA slice),
+//   C. waits until the W flags of that slice in its OWN buffer reach `step` (system-scope acquire),
 //   D. adds the W partial vectors in rank order (deterministic), applies scale + bias, writes the output.
 // Two buffer sets alternate by step parity: a rank can be at most one step ahead of any peer (it needs the peer's
 // flag of step s before it can finish s), so set (s+1)&1 is never still being read when it is overwritten.
@@ -16,7 +16,8 @@
 namespace aqlm_b200 {
 
 constexpr int kPeerMaxWorld = 16;
-constexpr int kPeerFlagBytes = 256;
+constexpr int kPeerMaxCtas = 16;
+constexpr int kPeerFlagBytes = kPeerMaxWorld * kPeerMaxCtas * 4;  // flag[src rank][cta slice]
 constexpr int kPeerThreads = 512;
 
 struct PeerParams {
@@ -55,42 +56,37 @@ template <typename T>
 __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_epilogue_kernel(const PeerParams p) {
   griddep_launch_dependents();
   griddep_wait();  // the partials come from the GEMV launched just before
-  __shared__ unsigned int s_flag;
   const unsigned int s = *p.step + 1u;  // the step this call completes (only this kernel's last CTA writes *step)
   const int set = (int)(s & 1u);
   const int n4 = p.n >> 2;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  // each CTA owns one contiguous slice of the vector end to end: push it, signal it, wait for it, reduce it
+  const int per = (n4 + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per, i1 = min(n4, i0 + per);
 
-  // ---- A: push my partials into every rank's slot [set][my rank] (own copy included: plain store) ----
+  // ---- A: push my slice into every rank's slot [set][my rank] (own copy included) ----
   const float4* loc = reinterpret_cast<const float4*>(p.local);
-  for (int i = gtid; i < n4; i += gsz) {
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     const float4 v = loc[i];
 #pragma unroll 1
     for (int r = 0; r < p.world; ++r)
       reinterpret_cast<float4*>(peer_slot(p.peer_base[r], p.max_elems, p.world, set, p.rank))[i] = v;
   }
-  // ---- B: when the whole grid has pushed, publish flag[my rank] = s on every rank ----
-  __threadfence_system();
+  // ---- B: CTA barrier, then thread r publishes flag[my rank][slice] = s on rank r with a system-scope RELEASE store
+  //      (cumulative over the whole CTA's stores through the barrier); C: thread r polls flag[r][slice] in MY buffer ----
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int old = atomicAdd(p.tickets + 0, 1u);
-    if (old == gridDim.x - 1) {
-      p.tickets[0] = 0u;
-      __threadfence_system();
-      for (int r = 0; r < p.world; ++r)
-        st_release_sys_u32(reinterpret_cast<unsigned int*>(p.peer_base[r]) + p.rank, s);
+  if ((int)threadIdx.x < p.world) {
+    const int r = threadIdx.x;
+    st_release_sys_u32(reinterpret_cast<unsigned int*>(p.peer_base[r]) + p.rank * kPeerMaxCtas + blockIdx.x, s);
+    const unsigned int* f = reinterpret_cast<const unsigned int*>(p.peer_base[p.rank]) + r * kPeerMaxCtas + blockIdx.x;
+    while ((int)(ld_acquire_sys_u32(f) - s) < 0) {
     }
-    // ---- C: wait for every source rank's flag in MY buffer ----
-    const unsigned int* myflags = reinterpret_cast<const unsigned int*>(p.peer_base[p.rank]);
-    for (int r = 0; r < p.world; ++r)
-      while ((int)(ld_acquire_sys_u32(myflags + r) - s) < 0) {
-      }
-    s_flag = 1u;
   }
   __syncthreads();
   // ---- D: fixed-order sum over source ranks + scale + bias ----
   T* y = reinterpret_cast<T*>(p.y);
-  for (int i = gtid; i < n4; i += gsz) {
+  const T* sc = reinterpret_cast<const T*>(p.scales);
+  const T* bi = reinterpret_cast<const T*>(p.bias);
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < p.world; ++r) {
       const float4 v = ld_cg_f4(reinterpret_cast<const float4*>(peer_slot(p.peer_base[p.rank], p.max_elems, p.world, set, r)) + i);
@@ -98,8 +94,6 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_epilogue_kernel(c
     }
     const int e = i << 2;
     const int o = e % p.out_features;  // out_features % 4 == 0, so the 4 elements share a batch row
-    const T* sc = reinterpret_cast<const T*>(p.scales);
-    const T* bi = reinterpret_cast<const T*>(p.bias);
     const float a[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -108,7 +102,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_epilogue_kernel(c
       y[e + u] = DT<T>::from_float(fmaf(a[u], sv, bv));
     }
   }
-  // ---- step bookkeeping: the last CTA to finish advances the local step counter ----
+  // ---- step bookkeeping (off the critical path): the last CTA to finish advances the local step counter ----
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int old = atomicAdd(p.tickets + 1, 1u);
