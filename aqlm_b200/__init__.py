@@ -12,6 +12,8 @@ from .inference import QuantizedLinear  # noqa: F401
 from .inference_kernels import optimize_for_training  # noqa: F401
 from .inference_kernels import cuda_kernel as _cuda_kernel  # noqa: F401  (registers the aqlm:: ops; no JIT build)
 
+from .grouped import QuantizedLinearGroup, ShardedQuantizedLinearGroup  # noqa: E402,F401
+
 __version__ = "1.1.6+b200.0.1"  # tracks the reference's aqlm 1.1.6 (inference_lib/setup.cfg:2-3)
 
 

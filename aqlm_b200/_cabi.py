@@ -76,6 +76,7 @@ def lib():
                 L.aqlm_b200_matmat.argtypes = [wp, vp, vp, i64, vp]
                 L.aqlm_b200_matmat_ex.argtypes = [wp, vp, vp, i64, u32, vp]
                 L.aqlm_b200_matmat_dequant.argtypes = [wp, vp, vp, i64, vp]
+                L.aqlm_b200_matmat_grouped.argtypes = [wp, ctypes.POINTER(i64), ctypes.c_int, vp, vp, i64, u32, vp]
                 L.aqlm_b200_matmat_workspace_bytes.argtypes = [wp, i64]
                 L.aqlm_b200_matmat_workspace_bytes.restype = ctypes.c_size_t
                 L.aqlm_b200_matmat_ws.argtypes = [wp, vp, vp, i64, u32, vp, ctypes.c_size_t, vp]

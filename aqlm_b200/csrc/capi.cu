@@ -211,6 +211,8 @@ static int matmat_typed(const aqlm_b200_weight_t* w, const void* input, void* ou
   p.nbits = w->nbits_per_codebook;
   p.num_codebooks = w->num_codebooks;
   p.partial_f32 = partial ? 1 : 0;
+  p.n_seg = 1;
+  p.seg_end[0] = p.seg_end[1] = p.seg_end[2] = p.seg_end[3] = p.out_features;
   const size_t out_elt = partial ? 4 : 2;
   // largest pass size whose x tile fits in shared memory
   int max_bt = 8;
@@ -584,6 +586,56 @@ int aqlm_b200_matmat_ws(const aqlm_b200_weight_t* w, const void* input, void* ou
     }
   }
   return aqlm_b200_matmat_ex(w, input, output, batch, flags, stream);
+}
+
+int aqlm_b200_matmat_grouped(const aqlm_b200_weight_t* w, const int64_t* seg_rows, int n_seg, const void* input,
+                             void* output, int64_t batch, uint32_t flags, void* stream) {
+  const bool partial = (flags & AQLM_B200_FLAG_PARTIAL_F32) != 0;
+  int rc = validate(w, !partial);
+  if (rc) return rc;
+  if (!seg_rows || n_seg < 1 || n_seg > 4) return fail(AQLM_B200_ERR_SHAPE, "grouped launch takes 1..4 segments");
+  if (w->num_codebooks != 1 || w->nbits_per_codebook != 16 || w->in_group_size != 8)
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "grouped launch is implemented for the 1x16 (in_group 8) scheme only");
+  if (batch < 1 || batch > 8) return fail(AQLM_B200_ERR_UNSUPPORTED, "grouped launch takes 1..8 batch rows");
+  if (!input || !output) return fail(AQLM_B200_ERR_SHAPE, "input/output pointer is NULL");
+  int64_t total = 0;
+  for (int i = 0; i < n_seg; ++i) total += seg_rows[i];
+  if (total != w->out_features) return fail(AQLM_B200_ERR_SHAPE, "segment rows do not add up to out_features");
+  const size_t row_bytes = (size_t)(w->in_features / 8) * 2;
+  if (row_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(w->codes) & 15) || (reinterpret_cast<uintptr_t>(input) & 15))
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "grouped launch needs 16-byte aligned code rows and input");
+  const DeviceInfo* di = device_info();
+  if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
+  GemvParams p;
+  p.codes = w->codes;
+  p.codebooks = w->codebooks;
+  p.scales = w->scales;
+  p.bias = w->bias;
+  p.x = input;
+  p.y = output;
+  p.out_features = (int)w->out_features;
+  p.in_features = (int)w->in_features;
+  p.in_groups = (int)(w->in_features / 8);
+  p.nbits = 16;
+  p.num_codebooks = 1;
+  p.batch = (int)batch;
+  p.partial_f32 = partial ? 1 : 0;
+  p.n_seg = n_seg;
+  int64_t acc = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (i < n_seg) acc += seg_rows[i];
+    p.seg_end[i] = (int)acc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int bt = batch == 1 ? 1 : (batch == 2 ? 2 : (batch <= 4 ? 4 : 8));
+  if (vec_smem_bytes(p, 1, 2, 8, bt, false, di->sm_count) > (size_t)di->max_smem_optin - 1024)
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "grouped launch: activation tile does not fit in shared memory");
+#define AQLM_GRP(T)                                                   \
+  (bt == 1 ? launch_1x16<T, 1, 0>(p, di, st) : bt == 2 ? launch_1x16<T, 2, 0>(p, di, st) \
+           : bt == 4 ? launch_1x16<T, 4, 0>(p, di, st) : launch_1x16<T, 8, 0>(p, di, st))
+  if (w->dtype == AQLM_B200_F16) return AQLM_GRP(__half);
+  return AQLM_GRP(__nv_bfloat16);
+#undef AQLM_GRP
 }
 
 int aqlm_b200_matmat(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, void* stream) {

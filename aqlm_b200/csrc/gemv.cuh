@@ -27,6 +27,10 @@ struct GemvParams {
   int num_codebooks;  // runtime K for the generic kernel
   int batch;          // rows in this pass (<= BT)
   int partial_f32;
+  // grouped launch (several linears sharing x, rows concatenated): segment i covers rows [seg_end[i-1], seg_end[i]) and
+  // uses the codebook at codebooks + i * (K << nbits) * g elements.  n_seg == 1 for a plain linear.
+  int n_seg;
+  int seg_end[4];
 };
 
 constexpr int kGemvThreads = 256;  // generic (fallback) kernel
@@ -224,9 +228,19 @@ __global__ void __launch_bounds__(kGemv1x16Threads, 1) gemv_1x16_kernel(const Ge
     const int row = (int)blockIdx.x + ri * (int)gridDim.x;
     return ld_stream_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.codes) + row * row_bytes) + c);
   };
-  auto gather = [&](const uint4& cw, uint4 (&w)[8]) {
+  // codebook of the segment that owns task t's row (grouped launches stack one 1 MiB codebook per segment)
+  auto task_codebook = [&](int t) -> const uint4* {
+    if (p.n_seg <= 1) return gcb;
+    const int row = (int)blockIdx.x + (t / slices) * (int)gridDim.x;
+    int seg = 0;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) w[e] = ld_gather_v4<GM>(gcb + chunk_code<2>(cw, e));
+    for (int i = 0; i < 3; ++i) seg += (i < p.n_seg - 1 && row >= p.seg_end[i]) ? 1 : 0;
+    return gcb + (size_t)seg * 65536;
+  };
+  auto gather = [&](int t, const uint4& cw, uint4 (&w)[8]) {
+    const uint4* cb = task_codebook(t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = ld_gather_v4<GM>(cb + chunk_code<2>(cw, e));
   };
   auto consume = [&](int t, bool live, const uint4 (&w)[8]) {
     float acc[BT];
@@ -253,7 +267,7 @@ __global__ void __launch_bounds__(kGemv1x16Threads, 1) gemv_1x16_kernel(const Ge
   uint4 wA[8], wB[8];
   uint4 cwA = load_codes(warp, liveA);
   uint4 cwB = load_codes(warp + kWarps, liveB);
-  if (liveA) gather(cwA, wA);
+  if (liveA) gather(warp, cwA, wA);
   griddep_wait();
   {
     const uint4* gx = reinterpret_cast<const uint4*>(p.x);
@@ -270,12 +284,12 @@ __global__ void __launch_bounds__(kGemv1x16Threads, 1) gemv_1x16_kernel(const Ge
 
   for (int t = warp; t < tasks; t += 2 * kWarps) {
     // A = task t (gathers already in flight), B = task t + kWarps (codes loaded)
-    if (liveB) gather(cwB, wB);
+    if (liveB) gather(t + kWarps, cwB, wB);
     bool liveA2;
     cwA = load_codes(t + 2 * kWarps, liveA2);
     consume(t, liveA, wA);
     liveA = liveA2;
-    if (liveA) gather(cwA, wA);
+    if (liveA) gather(t + 2 * kWarps, cwA, wA);
     const int tb = t + kWarps;
     bool liveB2;
     const bool haveB = tb < tasks;

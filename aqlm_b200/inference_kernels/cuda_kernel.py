@@ -164,6 +164,31 @@ def matmat_dequant(input, codes, codebooks, scales, bias=None) -> torch.Tensor:
     return flat_output.reshape(input.shape[:-1] + (w.out_features,))
 
 
+def matmat_grouped(input, codes, codebooks_stacked, scales, bias, seg_rows, partial: bool = False) -> torch.Tensor:
+    """ONE launch for several 1x16 linears sharing `input`: `codes` [sum(seg_rows), in/8, 1] (row-concatenated),
+    `codebooks_stacked` [n_seg, 1, 65536, 1, 8], `scales`/`bias` concatenated.  Returns [..., sum(seg_rows)] in the input
+    dtype, or UNSCALED fp32 partials when `partial` (sharded path)."""
+    device = _require_cuda(input, codes, codebooks_stacked, scales, bias)
+    _dtype_code(input)
+    n_seg = codebooks_stacked.shape[0]
+    if n_seg != len(seg_rows) or not codebooks_stacked.is_contiguous():
+        raise ValueError("codebooks_stacked must be a contiguous [n_seg, ...] stack matching seg_rows")
+    w = make_weight(codes, codebooks_stacked[0], None if partial else scales.reshape(-1), None if partial else bias)
+    if input.shape[-1] != w.in_features:
+        raise ValueError(f"input has {input.shape[-1]} features, weight expects {w.in_features}")
+    flat_input = input.reshape(-1, input.shape[-1])
+    if not flat_input.is_contiguous():
+        flat_input = flat_input.contiguous()
+    batch = flat_input.shape[0]
+    out = torch.empty((batch, w.out_features), dtype=torch.float32 if partial else input.dtype, device=device)
+    seg = (ctypes.c_int64 * n_seg)(*[int(r) for r in seg_rows])
+    with _on_device(device):
+        _cabi.check(_cabi.lib().aqlm_b200_matmat_grouped(ctypes.byref(w), seg, n_seg, flat_input.data_ptr(), out.data_ptr(),
+                                                         batch, _cabi.FLAG_PARTIAL_F32 if partial else 0,
+                                                         _stream_ptr(device)))
+    return out.reshape(input.shape[:-1] + (w.out_features,))
+
+
 def matmat_partial(input, codes, codebooks) -> torch.Tensor:
     """UNSCALED fp32 partial products [batch, out] of an in_features shard (to be all-reduced)."""
     device = _require_cuda(input, codes, codebooks)

@@ -216,6 +216,23 @@ def build_model(model, K, nbits, n_layers, device, rank, world, peer_comm=None):
     return layers
 
 
+def group_layers(layers, K, nbits, world):
+    """q/k/v and gate/up read the same activation: run each set as ONE grouped launch (and one exchange when sharded).
+    Returns per layer a list of (callable, in_features_local)."""
+    from aqlm_b200.grouped import QuantizedLinearGroup, ShardedQuantizedLinearGroup
+
+    out = []
+    for mods in layers:
+        ms = [m for m, _ in mods]
+        n_h, n_i = mods[0][1], mods[6][1]
+        if (K, nbits) == (1, 16):
+            G = QuantizedLinearGroup if world == 1 else ShardedQuantizedLinearGroup
+            out.append([(G(ms[0:3]), n_h), (ms[3], n_h), (G(ms[4:6]), n_h), (ms[6], n_i)])
+        else:
+            out.append([(m, n) for m, n in mods])
+    return out
+
+
 def secondary_metrics(device, peak_hbm):
     """Short extra measurements reported beside the headline (not part of `value`): the batch-256 fused dequant+tcgen05
     GEMM (BASELINE configs[3]) and the Kx8 LUT matvec (configs[2]).  CUDA-graph replay over rotating weight copies."""
@@ -317,6 +334,9 @@ def run_ours(args):
                 print(f"[bench] peer-memory communicator unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
                 peer_comm = None
     layers = build_model(model, K, nbits, n_layers, device, rank, world, peer_comm)
+    grouped = not args.no_group and (K, nbits) == (1, 16)
+    if grouped:
+        layers = group_layers(layers, K, nbits, world)
     in_sizes = sorted({n for mods in layers for _, n in mods})
     x_dev = {n: torch.randn((1, n), dtype=torch.float16, device=device) for n in in_sizes}
     x_host = {n: torch.randn((1, n), dtype=torch.float16).pin_memory() for n in in_sizes}
@@ -327,7 +347,7 @@ def run_ours(args):
         for mods in layers:
             for m, n in mods:
                 y = m(x_dev[n])
-        outs["y"] = y
+        outs["y"] = y[-1] if isinstance(y, tuple) else y
 
     # bind kernels / NCCL outside capture, count launches of one step
     step()
@@ -428,7 +448,7 @@ def run_ours(args):
     if rank == 0:
         value = total_bytes / (ms_step * 1e-3) / 1e9
         e2e_value = total_bytes / (ms_e2e * 1e-3) / 1e9
-        n_lin = n_layers * 7
+        n_lin = n_layers * (4 if grouped else 7)
         per_gpu_bytes = total_bytes / world
         avg_launch_us = ms_step * 1e3 / n_lin
         achieved = per_gpu_bytes / n_lin / (avg_launch_us * 1e-6) / 1e9
@@ -452,7 +472,9 @@ def run_ours(args):
             "config": {"workload": f"{model} {K}x{nbits} g8 all-linear matvec sweep, bs=1, {n_layers} layers x 7 linears",
                        "parallelism": "single GPU" if world == 1 else f"in_features-sharded x{world}, one exchange per linear: {reduce_kind}",
                        "l2_policy": f"inputs larger than L2: {total_bytes / world / 2**20:.0f} MiB of distinct codes per GPU per step",
-                       "cuda_graph": bool(use_graph), "code_bytes_per_step": total_bytes},
+                       "cuda_graph": bool(use_graph), "code_bytes_per_step": total_bytes,
+                       "grouped_launches": "q/k/v and gate/up each run as ONE grouped launch (QuantizedLinearGroup): 4 launches per layer"
+                       if grouped else "one launch per linear (7 per layer)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "gemv (fused code-gather + dequant + dot), avg over the step's launches incl. launch gaps",
@@ -500,6 +522,7 @@ def main():
     ap.add_argument("--scheme", default="1x16")
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only; invalidates the number)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-group", action="store_true", help="one launch per linear instead of grouped q/k/v and gate/up")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-n1", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true")

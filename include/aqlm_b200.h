@@ -83,6 +83,13 @@ size_t aqlm_b200_matmat_workspace_bytes(const aqlm_b200_weight_t* w, int64_t bat
 int aqlm_b200_matmat_ws(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, uint32_t flags,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Grouped launch for several 1x16 linears that share the same input (q/k/v, gate/up): `w` describes the ROW-CONCATENATED
+ * weights (codes [sum(seg_rows), in/8, 1], scales/bias [sum(seg_rows)]) and w->codebooks points to n_seg codebooks stacked
+ * back to back (1 MiB each); output is [batch, sum(seg_rows)].  One launch instead of n_seg; batch <= 8.  New work (the
+ * reference launches every linear separately); SURVEY §8f.2. */
+int aqlm_b200_matmat_grouped(const aqlm_b200_weight_t* w, const int64_t* seg_rows, int n_seg, const void* input,
+                             void* output, int64_t batch, uint32_t flags, void* stream);
+
 /* Fused dequant + tensor-core GEMM for large batch: W never goes to HBM.  Replaces
  * code{1x16,2x8,1x8}_matmat_dequant (cuda_kernel.cpp:249-301, 450-484, 615-649: Dequant kernel ->
  * full W in HBM -> cuBLAS F::linear -> epilogue). */

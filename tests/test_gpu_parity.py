@@ -385,3 +385,33 @@ def test_lut_gemv_kx8(K, fin, fout):
         case = dict(x=x.cpu().numpy(), codes=codes.cpu().numpy(), codebooks=codebooks.cpu().numpy(),
                     scales=scales.cpu().numpy(), bias=bias.cpu().numpy())
         assert O.relative_error(y.cpu().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
+
+
+# ---- grouped launch (q/k/v, gate/up) -----------------------------------------------------------------------------
+@pytest.mark.parametrize("batch", [1, 3, 8])
+def test_grouped_launch_equals_members(batch):
+    import aqlm_b200
+
+    outs = [512, 128, 128]
+    cases = [O.make_case(9100 + i, 1024, o, 1, 16, 8, batch, bias=True) for i, o in enumerate(outs)]
+    for c in cases[1:]:
+        c["x"] = cases[0]["x"]  # same activation
+    members, ts = zip(*[make_module(c, DEV) for c in cases])
+    before = {f"{i}.{k}": v.clone() for i, m in enumerate(members) for k, v in m.state_dict().items()}
+    group = aqlm_b200.QuantizedLinearGroup(list(members))
+    assert group.fused
+    # fusing re-points the members' parameters at views of the fused storage: values and state_dict layout unchanged
+    for i, m in enumerate(members):
+        for k, v in m.state_dict().items():
+            assert v.shape == before[f"{i}.{k}"].shape and torch.equal(v, before[f"{i}.{k}"])
+    assert sorted(group.state_dict().keys()) == sorted(f"members.{k}" for k in before)
+    x = ts[0]["x"]
+    ys = group(x)
+    assert len(ys) == 3
+    for m, c, y in zip(members, cases, ys):
+        assert torch.equal(y, m(x))  # same per-row arithmetic, bit-identical
+        assert O.relative_error(y.float().cpu().numpy(), oracle_output(c)) < TOL_FP16_TIGHT
+    # large batches fall back to the members (tensor-core op)
+    xb = torch.randn((16, 1024), dtype=torch.float16, device=DEV)
+    yb = group(xb)
+    assert yb[0].shape == (16, 512)
