@@ -409,7 +409,8 @@ def test_grouped_launch_equals_members(batch):
     ys = group(x)
     assert len(ys) == 3
     for m, c, y in zip(members, cases, ys):
-        assert torch.equal(y, m(x))  # same per-row arithmetic, bit-identical
+        if batch <= 6:  # members use the same GEMV arithmetic per row: bit-identical (above 6 rows they take the GEMM op)
+            assert torch.equal(y, m(x))
         assert O.relative_error(y.float().cpu().numpy(), oracle_output(c)) < TOL_FP16_TIGHT
     # large batches fall back to the members (tensor-core op)
     xb = torch.randn((16, 1024), dtype=torch.float16, device=DEV)
