@@ -33,6 +33,25 @@ def _worker(rank, world, port, ret):
                 y = m(t["x"])
             torch.cuda.synchronize()
             errs.append(O.relative_error(y.float().cpu().numpy(), oracle_output(case)))
+        # grouped: three linears sharing x -> ONE GEMV launch + ONE fused exchange
+        from aqlm_b200.grouped import ShardedQuantizedLinearGroup
+
+        cases = [O.make_case(5300 + i, 2048, o, 1, 16, 8, 1, bias=False) for i, o in enumerate((512, 128, 128))]
+        for c in cases[1:]:
+            c["x"] = cases[0]["x"]
+        ms = []
+        for c in cases:
+            t = to_torch(c, f"cuda:{rank}")
+            ms.append(ShardedQuantizedLinear.from_full(t["codes"], t["codebooks"], t["scales"], t["bias"], rank=rank,
+                                                       world_size=world, peer_comm=comm))
+        grp = ShardedQuantizedLinearGroup(ms)
+        assert grp.fused
+        x = to_torch(cases[0], f"cuda:{rank}")["x"]
+        for _ in range(2):
+            ys = grp(x)
+        torch.cuda.synchronize()
+        for c, y in zip(cases, ys):
+            errs.append(O.relative_error(y.float().cpu().numpy(), oracle_output(c)))
         ret[rank] = errs
     finally:
         dist.barrier()
