@@ -482,15 +482,18 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   p.codes = w->codes;
   p.row_bytes = (long long)(w->in_features / 8) * K * CB;
   const size_t smem = gemm_smem_layout(g.stages, g.n_tile).total;
-  auto kernel = gemm_dequant_kernel<T, K, CB>;
-  static std::atomic<size_t> configured{0};
-  if (configured.load(std::memory_order_relaxed) < smem) {
+  // producer mapping V2 (one 4-warp group per stage) measured: 1x16 496 vs 505 TFLOP/s (V1), 2x8 134 vs 394, 8x8 196 vs 119
+  // -> default only for schemes with many codebooks (profiles/r01/gemm_experiments.md)
+  const bool v2 = env_int("AQLM_B200_GEMM_V2", K >= 4 ? 1 : 0) != 0 && g.stages <= 3 && !(p.debug & 1);
+  auto kernel = v2 ? gemm_dequant_kernel<T, K, CB, true> : gemm_dequant_kernel<T, K, CB, false>;
+  static std::atomic<size_t> configured[2];
+  if (configured[v2].load(std::memory_order_relaxed) < smem) {
     AQLM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured.store(smem, std::memory_order_relaxed);
+    configured[v2].store(smem, std::memory_order_relaxed);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.m_tiles, g.ksplit, g.n_tiles);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(v2 ? kGemmThreadsV2 : kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

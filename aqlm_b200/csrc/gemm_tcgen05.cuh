@@ -24,6 +24,8 @@ namespace aqlm_b200 {
 
 constexpr int kGemmProducerWarps = 16;
 constexpr int kGemmThreads = 128 + 32 * kGemmProducerWarps;  // warps 0-3: TMA / MMA / TMEM-alloc, then epilogue; warps 4-19: dequant producers
+// V2 producer mapping: one 4-warp group per smem stage (at most 3 stages), each group owns every S-th k-block entirely
+constexpr int kGemmThreadsV2 = 128 + 32 * 4 * 3;
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;          // 64 halves = 128 bytes = one swizzle row
 constexpr int kCodeTileBytes = 128;      // bytes of codes per row per code tile (TMA box inner extent)
@@ -147,9 +149,10 @@ __host__ __device__ inline GemmSmem gemm_smem_layout(int stages, int n_tile) {
 
 // K = codebooks per group, CODE_BYTES = 1|2 ; in_group_size == 8.
 // bytes of codes per row per 64-wide k-block: GB = 8 groups * K * CODE_BYTES
-template <typename T, int K, int CODE_BYTES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <typename T, int K, int CODE_BYTES, bool V2>
+__global__ void __launch_bounds__(V2 ? kGemmThreadsV2 : kGemmThreads, 1)
 gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_codes, const GemmParams p) {
+  constexpr int NTHREADS = V2 ? kGemmThreadsV2 : kGemmThreads;
   constexpr int GB = 8 * K * CODE_BYTES;             // code bytes per row per k-block
   constexpr int KB_PER_CTILE = kCodeTileBytes / GB;  // k-blocks covered by one code tile
   static_assert(KB_PER_CTILE >= 1, "scheme too wide for the code tile");
@@ -183,12 +186,12 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), kGemmProducerWarps + 1);  // 8 producer warps + the TMA thread (expect_tx)
+      mbar_init(full_bar(s), (V2 ? 4 : kGemmProducerWarps) + 1);  // producer warps of the stage + the TMA thread (expect_tx)
       mbar_init(empty_bar(s), C);                      // tcgen05.commit of every CTA in the cluster
     }
     for (int s = 0; s < kCodeTileStages; ++s) {
       mbar_init(cfull_bar(s), 1);
-      mbar_init(cempty_bar(s), kGemmProducerWarps);
+      mbar_init(cempty_bar(s), V2 ? 4 * S : kGemmProducerWarps);
     }
     mbar_init(tfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -256,6 +259,121 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       }
       umma_commit(tfull_bar);  // accumulator complete
     } else if (warp >= 4) {
+      if constexpr (V2) {
+        // ===== V2 dequant producers: group g (4 warps, thread <-> row) owns stage g and every S-th k-block =====
+        const int pw = warp - 4;
+        const int g = pw >> 2;
+        if (g < S) {
+          const int row = (pw & 3) * 32 + lane;
+          const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
+          constexpr int CWN = GB / 4 > 0 ? GB / 4 : 1;  // 32-bit words of codes per row per k-block
+          constexpr bool INREG = (K <= 2);               // gather in issue() and hold the vectors in registers
+          constexpr bool DB = (K == 1);                  // double-buffer across k-blocks
+          int next_release = ct0;
+          // arrive on cempty for every code tile in [next_release, upto): each producer warp arrives exactly once per
+          // tile, in order, after the tile was loaded (phase bookkeeping) and after its own reads of it were consumed
+          auto release_upto = [&](int upto) {
+            for (; next_release < upto; ++next_release) {
+              const int cs = (next_release - ct0) % kCodeTileStages, cit = (next_release - ct0) / kCodeTileStages;
+              mbar_wait(cfull_bar(cs), cit & 1);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(cempty_bar(cs));
+            }
+          };
+          auto load_cw = [&](int i, uint32_t (&cw)[CWN]) {
+            const int kb = kb0 + i;
+            const int ct = kb / KB_PER_CTILE, st_in = kb % KB_PER_CTILE;
+            release_upto(ct);
+            const int cs = (ct - ct0) % kCodeTileStages, cit = (ct - ct0) / kCodeTileStages;
+            mbar_wait(cfull_bar(cs), cit & 1);
+            const uint8_t* crow = gbase + L.codes + cs * kGemmBlockM * kCodeTileBytes + row * 128;
+            if constexpr (GB >= 16) {
+#pragma unroll
+              for (int q = 0; q < GB / 16; ++q) {
+                const int chunk = ((st_in * GB) / 16 + q) ^ (row & 7);
+                const uint4 v = *reinterpret_cast<const uint4*>(crow + (chunk << 4));
+                cw[q * 4 + 0] = v.x; cw[q * 4 + 1] = v.y; cw[q * 4 + 2] = v.z; cw[q * 4 + 3] = v.w;
+              }
+            } else {  // GB == 8 (1x8)
+              const int lb = st_in * GB;
+              const int chunk = (lb >> 4) ^ (row & 7);
+              const uint2 v = *reinterpret_cast<const uint2*>(crow + (chunk << 4) + (lb & 15));
+              cw[0] = v.x; cw[1] = v.y;
+            }
+          };
+          auto code_at = [&](const uint32_t (&cw)[CWN], int idx) -> uint32_t {
+            if constexpr (CODE_BYTES == 2) return (cw[idx >> 1] >> ((idx & 1) * 16)) & 0xffffu;
+            else return (cw[idx >> 2] >> ((idx & 3) * 8)) & 0xffu;
+          };
+          auto gather_all = [&](const uint32_t (&cw)[CWN], uint4 (&wv)[8][INREG ? K : 1]) {
+            if constexpr (INREG) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                  const uint4* gp = gcb + (((size_t)k << p.nbits) + code_at(cw, e * K + k));
+                  if (p.gather_mode == 1) wv[e][k] = ld_gather_v4<1>(gp);
+                  else wv[e][k] = ld_gather_v4<0>(gp);
+                }
+            }
+          };
+          auto commit = [&](int i, const uint32_t (&cw)[CWN], uint4 (&wv)[8][INREG ? K : 1]) {
+            const int s = i % S, it = i / S;
+            if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
+            uint8_t* arow = gbase + L.a + s * kGemmBlockM * 128 + row * 128;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              uint4 v;
+              if constexpr (K == 1) {
+                v = wv[e][0];
+              } else {
+                float f[8];
+                if constexpr (INREG) {
+                  unpack8<T>(wv[e][0], f);
+#pragma unroll
+                  for (int k = 1; k < K; ++k) accum8<T>(wv[e][k], f);
+                } else {  // many codebooks: gather group by group (the 4-32 KiB codebooks are L1-resident)
+                  uint4 t[K];
+#pragma unroll
+                  for (int k = 0; k < K; ++k) t[k] = ld_gather_v4<0>(gcb + (((size_t)k << p.nbits) + code_at(cw, e * K + k)));
+                  unpack8<T>(t[0], f);
+#pragma unroll
+                  for (int k = 1; k < K; ++k) accum8<T>(t[k], f);
+                }
+                v.x = DT<T>::pack2(f[0], f[1]); v.y = DT<T>::pack2(f[2], f[3]);
+                v.z = DT<T>::pack2(f[4], f[5]); v.w = DT<T>::pack2(f[6], f[7]);
+              }
+              *reinterpret_cast<uint4*>(arow + ((e ^ (row & 7)) << 4)) = v;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(s));
+          };
+          if constexpr (DB) {
+            uint32_t ca[CWN], cb[CWN];
+            uint4 wa[8][K], wb[8][K];
+            int i = g;
+            if (i < nkb) { load_cw(i, ca); gather_all(ca, wa); }
+            for (; i < nkb; i += 2 * S) {
+              if (i + S < nkb) { load_cw(i + S, cb); gather_all(cb, wb); }
+              commit(i, ca, wa);
+              if (i + S < nkb) {
+                if (i + 2 * S < nkb) { load_cw(i + 2 * S, ca); gather_all(ca, wa); }
+                commit(i + S, cb, wb);
+              }
+            }
+          } else {
+            uint32_t ca[CWN];
+            uint4 wa[8][INREG ? K : 1];
+            for (int i = g; i < nkb; i += S) {
+              load_cw(i, ca);
+              gather_all(ca, wa);
+              commit(i, ca, wa);
+            }
+          }
+          release_upto(ct1);
+        }
+      } else {
       // ===== dequant producers: 512 threads, thread -> (row, quarter of the 8 groups of a k-block) =====
       // Software-pipelined: the gathers of k-block i+1 are in flight while k-block i is written to smem.
       const int pt = threadIdx.x - 128;
@@ -360,6 +478,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           }
         }
       }
+      }
     }
   }
 
@@ -420,7 +539,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const float* parts = p.ws_partials + (tile_id * p.ksplit) * (size_t)N * kGemmBlockM;
       const int rrow = threadIdx.x & (kGemmBlockM - 1);
       const int cphase = threadIdx.x >> 7;
-      constexpr int kPhases = kGemmThreads / kGemmBlockM;
+      constexpr int kPhases = NTHREADS / kGemmBlockM;
       const int row = m0 + rrow;
       if (row < p.out_features) {
         const float sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
