@@ -273,7 +273,7 @@ static LutPlan lut_plan(const aqlm_b200_weight_t* w, int64_t batch, const Device
   L.J = (K == 8) ? 16 : 32;
   const int in_groups = (int)(w->in_features / 8);
   L.n_slabs = (in_groups + L.J - 1) / L.J;
-  L.smem = (size_t)K * 256 * L.J * 4;
+  L.smem = (size_t)K * 256 * L.J * 4 + 16;  // LUT + the "last CTA" flag word
   if (L.smem + 1024 > (size_t)di->max_smem_optin) return L;
   int per_sm = (int)((size_t)di->max_smem_optin / (L.smem + 1024));
   const int want = env_int("AQLM_B200_LUT_CTAS_PER_SM", 2);  // 128 regs x 256 threads: registers allow 2

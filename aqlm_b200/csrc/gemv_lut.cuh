@@ -49,8 +49,10 @@ __device__ __forceinline__ void mma_m16n8k8(float (&d)[4], uint32_t a0, uint32_t
 
 // K codebooks, J groups per slab (32 -> one row per warp step, 16 -> two rows per warp step)
 template <typename T, int K, int J, int kLutThreads>
-__global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p) {
-  extern __shared__ __align__(16) float lut[];  // [K][256][J]
+__global__ void __launch_bounds__(kLutThreads, (kLutThreads == 256) ? 2 : 1) gemv_lut_kernel(const LutParams p) {
+  // [K][256][J] fp32 LUT at shared-memory offset 0 (the kernel has NO static shared memory), so a lookup address is
+  // just (code << log2(4J)) | lane_constant; one extra word after the LUT holds the "last CTA" flag
+  extern __shared__ __align__(16) float lut[];
   constexpr int NT = J / 8;                     // n-tiles (8 groups each) per slab
   constexpr int RPW = 32 / J;                   // rows per warp step
   constexpr int kWarps = kLutThreads / 32;
@@ -66,25 +68,34 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
   const bool g_ok = g < p.in_groups;
   const size_t row_bytes = (size_t)p.in_groups * K;
   const uint8_t* cbase = reinterpret_cast<const uint8_t*>(p.codes) + (size_t)g * K;
-  const float* lbase = lut + jj;
+  const uint32_t lane_off = (uint32_t)jj * 4u;
   const int row_begin = rb * p.rows_per_block;
   const int row_end = min(p.out_features, row_begin + p.rows_per_block);
   constexpr int RB = J;  // values per lane per batch; the butterfly leaves one row total per lane
   constexpr int CWN = (K + 3) / 4;
   float* part = p.ws_partials + (size_t)slab * p.out_features;
 
+  auto load_one = [&](const uint8_t* src, uint32_t (&c)[CWN]) {
+    if constexpr (K == 1) c[0] = (uint32_t)__ldg(src);
+    else if constexpr (K == 2) c[0] = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(src));
+    else if constexpr (K == 4) c[0] = __ldg(reinterpret_cast<const uint32_t*>(src));
+    else {
+      const uint2 t2 = __ldg(reinterpret_cast<const uint2*>(src));
+      c[0] = t2.x; c[1] = t2.y;
+    }
+  };
   auto load_codes = [&](int r0, uint32_t (&cw)[RB][CWN]) {
+    const uint8_t* src = cbase + (size_t)(r0 + rsub) * row_bytes;
+    const size_t stride = (size_t)RPW * row_bytes;
+    if (g_ok && r0 + RB * RPW <= row_end) {  // fast path: whole batch in range, no per-row predicates
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int row = r0 + i * RPW + rsub;
-      const bool ok = g_ok && row < row_end;
-      const uint8_t* src = cbase + (size_t)row * row_bytes;
-      if constexpr (K == 1) cw[i][0] = ok ? (uint32_t)__ldg(src) : 0u;
-      else if constexpr (K == 2) cw[i][0] = ok ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(src)) : 0u;
-      else if constexpr (K == 4) cw[i][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
-      else {
-        uint2 t2 = ok ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0u, 0u);
-        cw[i][0] = t2.x; cw[i][1] = t2.y;
+      for (int i = 0; i < RB; ++i, src += stride) load_one(src, cw[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < RB; ++i, src += stride) {
+#pragma unroll
+        for (int q = 0; q < CWN; ++q) cw[i][q] = 0u;
+        if (g_ok && r0 + i * RPW + rsub < row_end) load_one(src, cw[i]);
       }
     }
   };
@@ -160,8 +171,14 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const uint32_t c = (cw[i][k >> 2] >> ((k & 3) * 8)) & 0xffu;
-        acc += lbase[(size_t)(k * 256 + c) * J];  // rows/groups out of range hold code 0: harmless, never stored
+        // address = (code * 4J) | lane_off + k * 256 * 4J : shift + (and|or) + LDS with an immediate offset
+        constexpr int SH = (J == 32) ? 7 : 6;  // log2(4 * J)
+        const int bit = (k & 3) * 8;
+        const uint32_t w = cw[i][k >> 2];
+        const uint32_t sh = bit >= SH ? (w >> (bit - SH)) : (w << (SH - bit));
+        const uint32_t off = (sh & (0xffu << SH)) | lane_off;  // byte offset inside codebook k's LUT
+        acc += *reinterpret_cast<const float*>(reinterpret_cast<const char*>(lut) + (size_t)k * 256 * 4 * J + off);
+        // (rows/groups out of range hold code 0: harmless, never stored)
       }
       v[i] = acc;
     }
@@ -189,14 +206,14 @@ __global__ void __launch_bounds__(kLutThreads) gemv_lut_kernel(const LutParams p
   // ---------------- fix-up: the last slab CTA of this row block adds the slabs in order ----------------
   __threadfence();
   __syncthreads();
-  __shared__ unsigned int s_last;
+  unsigned int* s_last = reinterpret_cast<unsigned int*>(lut + (size_t)K * 256 * J);
   if (tid == 0) {
     const unsigned int old = atomicAdd(p.ws_counters + rb, 1u);
-    s_last = (old == (unsigned int)p.n_slabs - 1) ? 1u : 0u;
-    if (s_last) p.ws_counters[rb] = 0u;
+    *s_last = (old == (unsigned int)p.n_slabs - 1) ? 1u : 0u;
+    if (*s_last) p.ws_counters[rb] = 0u;
   }
   __syncthreads();
-  if (s_last) {
+  if (*s_last) {
     __threadfence();
     for (int row = row_begin + tid; row < row_end; row += kLutThreads) {
       float acc = 0.f;

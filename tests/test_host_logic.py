@@ -163,3 +163,51 @@ def test_install_as_aqlm_alias():
         for k in [k for k in sys.modules if k == "aqlm" or k.startswith("aqlm.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_group_on_cpu_keeps_members_and_state_dict():
+    """Grouping never changes what state_dict exposes; without CUDA tensors nothing is fused (and nothing computes)."""
+    ms = [aqlm_b200.QuantizedLinear(64, o, 8, 1, 1, 16, bias=False, dtype=torch.float16) for o in (32, 8, 8)]
+    grp = aqlm_b200.QuantizedLinearGroup(ms)
+    assert not grp.fused and grp.seg_rows == [32, 8, 8]
+    keys = sorted(grp.state_dict().keys())
+    assert keys == sorted(f"members.{i}.{n}" for i in range(3) for n in ("codebooks", "codes", "scales"))
+    with pytest.raises(NotImplementedError):
+        grp(torch.zeros(1, 64, dtype=torch.float16))
+    with pytest.raises(ValueError):
+        aqlm_b200.QuantizedLinearGroup([ms[0], aqlm_b200.QuantizedLinear(128, 8, 8, 1, 1, 16, bias=False,
+                                                                         dtype=torch.float16)])
+
+
+def test_c_abi_grouped_and_comm_argument_checks_without_gpu():
+    L = _cabi.lib()
+    w = _cabi.Weight()
+    w.codes, w.codebooks, w.scales = 16, 16, 16
+    w.in_features, w.out_features = 64, 48
+    w.num_codebooks, w.nbits_per_codebook, w.in_group_size, w.out_group_size = 2, 8, 8, 1
+    w.dtype = _cabi.F16
+    seg = (ctypes.c_int64 * 3)(32, 8, 8)
+    # grouped launches exist for 1x16 only
+    assert L.aqlm_b200_matmat_grouped(ctypes.byref(w), seg, 3, 16, 16, 1, 0, None) == _cabi.ERR_UNSUPPORTED
+    w.num_codebooks, w.nbits_per_codebook = 1, 16
+    bad = (ctypes.c_int64 * 3)(32, 8, 7)
+    assert L.aqlm_b200_matmat_grouped(ctypes.byref(w), bad, 3, 16, 16, 1, 0, None) == _cabi.ERR_SHAPE
+    assert L.aqlm_b200_matmat_grouped(ctypes.byref(w), seg, 5, 16, 16, 1, 0, None) == _cabi.ERR_SHAPE
+    assert L.aqlm_b200_matmat_grouped(ctypes.byref(w), seg, 3, 16, 16, 9, 0, None) == _cabi.ERR_UNSUPPORTED
+    # communicator sizing is pure arithmetic
+    assert L.aqlm_b200_comm_shared_bytes(8, 1024) == 1024 + 2 * 8 * 1024 * 4
+    assert L.aqlm_b200_comm_shared_bytes(0, 1024) == 0 and L.aqlm_b200_comm_shared_bytes(17, 1024) == 0
+    assert L.aqlm_b200_allreduce_scale_bias(None, None, None, None, None, 1, 4, 0, None) == _cabi.ERR_SHAPE
+
+
+def test_workspace_queries_are_zero_without_a_device():
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without CUDA")
+    L = _cabi.lib()
+    w = _cabi.Weight()
+    w.codes, w.codebooks, w.scales = 16, 16, 16
+    w.in_features, w.out_features = 4096, 4096
+    w.num_codebooks, w.nbits_per_codebook, w.in_group_size, w.out_group_size = 2, 8, 8, 1
+    w.dtype = _cabi.F16
+    assert L.aqlm_b200_matmat_workspace_bytes(ctypes.byref(w), 1) == 0
+    assert L.aqlm_b200_matmat_dequant_workspace_bytes(ctypes.byref(w), 256) == 0
