@@ -101,17 +101,18 @@ class _on_device:
             self.ctx.__exit__(*exc)
 
 
-_WORKSPACES: dict = {}  # device index -> persistent zero-initialised workspace (ticket counters stay zero)
+_WORKSPACES: dict = {}  # (device index, stream handle) -> persistent zero-initialised workspace
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Persistent per-device workspace for the split-K GEMM and the LUT GEMV.  The kernels leave the ticket counters at
-    zero, so the buffer is zeroed only when it is (re)allocated.  One workspace per device: concurrent use from several
-    streams of the same device is not supported."""
-    ws = _WORKSPACES.get(device.index)
+    """Persistent workspace for the split-K GEMM and the LUT GEMV, one per (device, stream): kernels on different streams
+    never share ticket counters or partials.  The kernels leave the counters at zero, so a buffer is zeroed only when it
+    is (re)allocated."""
+    key = (device.index, _stream_ptr(device))
+    ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 4 << 20), dtype=torch.uint8, device=device)
-        _WORKSPACES[device.index] = ws
+        _WORKSPACES[key] = ws
     return ws
 
 
