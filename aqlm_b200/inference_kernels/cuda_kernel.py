@@ -108,7 +108,11 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     """Persistent workspace for the split-K GEMM and the LUT GEMV, one per (device, stream): kernels on different streams
     never share ticket counters or partials.  The kernels leave the counters at zero, so a buffer is zeroed only when it
     is (re)allocated."""
-    key = (device.index, _stream_ptr(device))
+    # While a CUDA graph is being captured, use the device-level buffer (key 0 = the default stream's), which the
+    # warm-up call outside the capture allocated from the normal pool: a buffer allocated INSIDE a capture would live in
+    # that graph's private pool and dangle once the graph is destroyed.
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (device.index, 0 if capturing else _stream_ptr(device))
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 4 << 20), dtype=torch.uint8, device=device)
