@@ -399,6 +399,7 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   if (allow_split) {
     // The kernel is bound by the per-SM codebook-gather rate, so what matters is how many SMs gather.  Model:
     //   t(ks) = gather_time / sm_efficiency(ks) + split-K fix-up traffic (partials written + read once through L2)
+    //           + waves * fixed per-CTA cost      (checked against a measured sweep, profiles/r01/gemm_experiments.md)
     const double tiles = (double)g.m_tiles * g.n_tiles;
     const double gathers = (double)w->out_features * (w->in_features / 8) * K * g.n_tiles;
     const double t_gather = gathers / 250e9;  // measured chip-wide 16-byte gather rate (profiles/r01/gather_microbench_v1.jsonl)
@@ -409,7 +410,8 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
       const double waves = (double)((long long)((ctas + di->sm_count - 1) / di->sm_count));
       const double eff = ctas / (waves * di->sm_count);
       const double fix = c > 1 ? ctas * g.n_tile * kGemmBlockM * 4.0 * 2.0 / 4e12 : 0.0;
-      const double t = t_gather / eff + fix;
+      // every wave pays the CTA's fixed costs again (launch ramp, TMEM alloc, pipeline fill, epilogue): ~5 us measured
+      const double t = t_gather / eff + fix + waves * 5e-6;
       if (t < best * 0.97) {  // prefer fewer splits unless the gain is real
         best = t;
         ks = c;
