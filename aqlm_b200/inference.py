@@ -1,25 +1,49 @@
-"""`QuantizedLinear` -- the module API of the hot path (reference inference_lib/src/aqlm/inference.py:11-142).
+"""`QuantizedLinear`: the module-level API of the AQLM hot path, CUDA (sm_100a) only.
 
-Same constructor signature, parameter names, shapes and dtypes (inference.py:12-61), same lazy kernel binding and
-gemv/gemm dispatch rule (68-96), same autograd wrapper (99-142), so Hugging Face's AQLM integration
-(`replace_with_aqlm_linear`) can construct it on the meta device and load a checkpoint by name.
-Differences from the reference: CUDA only (CPU inputs raise; the reference's in-place CPU permutation of `codes`,
-inference.py:78-83, does not exist here, so `state_dict()` never changes shape), and no JIT build on first call.
+Public contract kept from the reference module (inference_lib/src/aqlm/inference.py:11-142), because Hugging Face's AQLM
+integration and existing checkpoints depend on it:
+  * constructor `QuantizedLinear(in_features, out_features, in_group_size, out_group_size, num_codebooks,
+    nbits_per_codebook, bias=True, device=None, dtype=None)` (inference.py:12-23), also on the meta device;
+  * frozen parameters `codebooks [K, 2^nbits, og, ig]`, `codes [out/og, in/ig, K]` (signed storage of unsigned codes),
+    `scales [out/og, 1, 1, 1]`, optional `bias [out]` (inference.py:39-61) -- the state_dict names / shapes / dtypes;
+  * small inputs (<= 6 rows, inference.py:95-96) go to the fused GEMV op, larger ones to the fused dequant + tensor-core
+    GEMM op; gradients flow to the input only (inference.py:99-142).
+What differs: no CPU path (CPU inputs raise), no in-place re-layout of `codes` on first use (inference.py:78-83), no JIT
+build on first call -- the ops are bound once and cached.
 """
 from __future__ import annotations
 
 import math
-from typing import Any, Optional
+from typing import Callable, Optional, Tuple
 
 import torch
-import torch.nn as nn
+from torch import nn
 
 from .inference_kernels import get_backward_pass_kernel, get_forward_pass_kernel
 from .utils import get_int_dtype
 
-# Batch rows (prod of leading dims) up to which the fused GEMV kernel is used; above it the fused
-# dequant+GEMM op runs.  The reference uses 6 (inference.py:95-96).
+#: largest number of input rows (product of the leading dims) served by the GEMV op; same threshold as the reference
 GEMV_MAX_ROWS = 6
+
+
+class _AqlmMatmul(torch.autograd.Function):
+    """y = op(x; codes, codebooks, scales, bias).  Only `x` receives a gradient; the quantized weight is frozen."""
+
+    @staticmethod
+    def forward(ctx, x, codes, codebooks, scales, bias, forward_op: Callable, backward_op: Callable):
+        ctx.backward_op = backward_op
+        ctx.save_for_backward(codes, codebooks, scales, bias)
+        return forward_op(x, codes, codebooks, scales, bias)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        codes, codebooks, scales, bias = ctx.saved_tensors
+        grad_x = ctx.backward_op(grad_y, codes, codebooks, scales, bias)
+        return grad_x, None, None, None, None, None, None
+
+
+def _frozen(shape, **kwargs) -> nn.Parameter:
+    return nn.Parameter(torch.empty(shape, **kwargs), requires_grad=False)
 
 
 class QuantizedLinear(nn.Module):
@@ -35,83 +59,60 @@ class QuantizedLinear(nn.Module):
         device=None,
         dtype=None,
     ):
-        factory_kwargs = {"device": device, "dtype": dtype}
         super().__init__()
-        self.in_features = in_features
-        self.out_features = out_features
+        if in_features % in_group_size or out_features % out_group_size:
+            raise AssertionError(f"features ({in_features}, {out_features}) must be multiples of the group sizes "
+                                 f"({in_group_size}, {out_group_size})")
+        self.in_features, self.out_features = in_features, out_features
+        self.in_group_size, self.out_group_size = in_group_size, out_group_size
+        self.num_codebooks, self.nbits_per_codebook = num_codebooks, nbits_per_codebook
+        self.codebook_size = 1 << nbits_per_codebook
+        out_groups, in_groups = out_features // out_group_size, in_features // in_group_size
 
-        assert self.in_features % in_group_size == 0
-        assert self.out_features % out_group_size == 0
-        num_out_groups = out_features // out_group_size
-        num_in_groups = in_features // in_group_size
-        self.out_group_size, self.in_group_size = out_group_size, in_group_size
-        self.num_codebooks = num_codebooks
-        self.nbits_per_codebook = nbits_per_codebook
-        self.codebook_size = 2**nbits_per_codebook
-
-        # [num_codebooks, codebook_size, out_group_size, in_group_size]
-        self.codebooks = nn.Parameter(
-            torch.empty((num_codebooks, self.codebook_size, out_group_size, in_group_size), **factory_kwargs),
-            requires_grad=False,
-        )
-        # [num_out_groups, num_in_groups, num_codebooks], signed storage of unsigned codes (utils.pack_int_data)
-        self.codes = nn.Parameter(
-            torch.empty((num_out_groups, num_in_groups, num_codebooks), device=device,
-                        dtype=get_int_dtype(nbits_per_codebook)),
-            requires_grad=False,
-        )
-        # [num_out_groups, 1, 1, 1]
-        self.scales = nn.Parameter(torch.empty((num_out_groups, 1, 1, 1), **factory_kwargs), requires_grad=False)
+        self.codebooks = _frozen((num_codebooks, self.codebook_size, out_group_size, in_group_size), device=device,
+                                 dtype=dtype)
+        self.codes = _frozen((out_groups, in_groups, num_codebooks), device=device,
+                             dtype=get_int_dtype(nbits_per_codebook))
+        self.scales = _frozen((out_groups, 1, 1, 1), device=device, dtype=dtype)
         if bias:
-            self.bias = nn.Parameter(torch.empty(out_features, **factory_kwargs), requires_grad=False)
+            self.bias = _frozen((out_features,), device=device, dtype=dtype)
         else:
             self.register_parameter("bias", None)
+        self._ops: Optional[Tuple[Callable, Callable, Callable, Callable]] = None  # (gemv fwd, gemv bwd, gemm fwd, gemm bwd)
 
-        self.gemv_op = None
-        self.gemm_op = None
-        self.use_gemv_rule = None
-
-    def forward(self, input: torch.Tensor) -> torch.Tensor:
-        if self.gemv_op is None:
-            self.prepare_matmul_op(input)
-        if self.use_gemv_rule(input):
-            return self.gemv_op.apply(input, self.codes, self.codebooks, self.scales, self.bias)
-        return self.gemm_op.apply(input, self.codes, self.codebooks, self.scales, self.bias)
-
-    def prepare_matmul_op(self, input: torch.Tensor):
+    # -- kernel binding ---------------------------------------------------------------------------------------------
+    def prepare_matmul_op(self, input: torch.Tensor) -> None:
+        """Bind the four ops for this module's scheme (reference inference.py:77-96).  CUDA only."""
         if not input.is_cuda:
             raise NotImplementedError(
                 f"aqlm_b200.QuantizedLinear runs on CUDA (sm_100a) only; got input on {input.device}. "
                 "There is no CPU fallback in this package.")
-        self.gemv_op = _get_autograd_matmul_op(
-            get_forward_pass_kernel(self.codebooks, False),
-            get_backward_pass_kernel(self.codebooks, False),
-        )
-        self.gemm_op = _get_autograd_matmul_op(
-            get_forward_pass_kernel(self.codebooks, True),
-            get_backward_pass_kernel(self.codebooks, True),
-        )
-        self.use_gemv_rule = lambda input: math.prod(input.shape[:-1]) <= GEMV_MAX_ROWS
+        self._ops = tuple(select(self.codebooks, large_batch)
+                          for large_batch in (False, True)
+                          for select in (get_forward_pass_kernel, get_backward_pass_kernel))
+
+    # names kept for code that pokes at the reference's attributes
+    @property
+    def gemv_op(self):
+        return None if self._ops is None else self._ops[0]
+
+    @property
+    def gemm_op(self):
+        return None if self._ops is None else self._ops[2]
+
+    def use_gemv_rule(self, input: torch.Tensor) -> bool:
+        return math.prod(input.shape[:-1]) <= GEMV_MAX_ROWS
+
+    # -- forward ----------------------------------------------------------------------------------------------------
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        if self._ops is None:
+            self.prepare_matmul_op(input)
+        fwd, bwd = self._ops[:2] if self.use_gemv_rule(input) else self._ops[2:]
+        if not (torch.is_grad_enabled() and input.requires_grad):
+            return fwd(input, self.codes, self.codebooks, self.scales, self.bias)  # inference: skip the autograd node
+        return _AqlmMatmul.apply(input, self.codes, self.codebooks, self.scales, self.bias, fwd, bwd)
 
     def extra_repr(self) -> str:
         return (f"in_features={self.in_features}, out_features={self.out_features}, "
                 f"scheme={self.num_codebooks}x{self.nbits_per_codebook}, in_group_size={self.in_group_size}, "
                 f"bias={self.bias is not None}")
-
-
-def _get_autograd_matmul_op(forward_pass_kernel, backward_pass_kernel):
-    """reference inference.py:99-142: forward = kernel, backward = grad w.r.t. the input only."""
-
-    class _QuantizedMatmul(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx: Any, input: torch.Tensor, codes: torch.Tensor, codebooks: torch.Tensor,
-                    scales: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-            ctx.save_for_backward(input, codes, codebooks, scales, bias)
-            return forward_pass_kernel(input, codes, codebooks, scales, bias)
-
-        @staticmethod
-        def backward(ctx, grad_output: torch.Tensor):
-            input, codes, codebooks, scales, bias = ctx.saved_tensors
-            return (backward_pass_kernel(grad_output, codes, codebooks, scales, bias), None, None, None, None)
-
-    return _QuantizedMatmul
