@@ -122,11 +122,11 @@ static int launch_vec(const GemvParams& p, const DeviceInfo* di, cudaStream_t st
   return AQLM_B200_OK;
 }
 
-template <typename T, int BT, int GM>
-static int launch_1x16(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
-  const int grid = di->sm_count;
+template <typename T, int BT, int GM, int THREADS>
+static int launch_1x16_t(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
+  const int grid = di->sm_count * (512 / THREADS);
   const size_t smem = vec_smem_bytes(p, 1, 2, 8, BT, false, grid);
-  auto kernel = gemv_1x16_kernel<T, BT, GM>;
+  auto kernel = gemv_1x16_kernel<T, BT, GM, THREADS>;
   static std::atomic<size_t> configured{0};
   if (configured.load(std::memory_order_relaxed) < smem) {
     int rc = set_smem(kernel, smem);
@@ -135,7 +135,7 @@ static int launch_1x16(const GemvParams& p, const DeviceInfo* di, cudaStream_t s
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemv1x16Threads);
+  cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -146,6 +146,15 @@ static int launch_1x16(const GemvParams& p, const DeviceInfo* di, cudaStream_t s
   AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
   count_launch();
   return AQLM_B200_OK;
+}
+
+// 512-thread CTAs, one per SM (default), or 256-thread CTAs, two per SM (AQLM_B200_GEMV_THREADS=256; batch 1 only)
+template <typename T, int BT, int GM>
+static int launch_1x16(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
+  if constexpr (BT == 1 && GM == 0) {
+    if (env_int("AQLM_B200_GEMV_THREADS", kGemv1x16Threads) == 256) return launch_1x16_t<T, BT, GM, 256>(p, di, st);
+  }
+  return launch_1x16_t<T, BT, GM, kGemv1x16Threads>(p, di, st);
 }
 
 template <typename T, int CB, int G, int BT>

@@ -201,10 +201,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemv_vec_kernel(const GemvParams p
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGemv1x16Threads = 512;
 
-template <typename T, int BT, int GM>
-__global__ void __launch_bounds__(kGemv1x16Threads, 1) gemv_1x16_kernel(const GemvParams p) {
+template <typename T, int BT, int GM, int THREADS = kGemv1x16Threads>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) gemv_1x16_kernel(const GemvParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr int THREADS = kGemv1x16Threads;
   constexpr int kWarps = THREADS / 32;
   const int upr = p.in_features >> 3;
   griddep_launch_dependents();
