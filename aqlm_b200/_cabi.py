@@ -73,6 +73,7 @@ def lib():
                 L.aqlm_b200_version.restype = ctypes.c_int
                 L.aqlm_b200_last_error.restype = ctypes.c_char_p
                 L.aqlm_b200_launch_count.restype = ctypes.c_uint64
+                L.aqlm_b200_reload_tunables.restype = None
                 L.aqlm_b200_matmat.argtypes = [wp, vp, vp, i64, vp]
                 L.aqlm_b200_matmat_ex.argtypes = [wp, vp, vp, i64, u32, vp]
                 L.aqlm_b200_matmat_dequant.argtypes = [wp, vp, vp, i64, vp]
@@ -128,6 +129,11 @@ def check(status: int) -> None:
     if status == ERR_SHAPE:
         raise ValueError(msg)
     raise RuntimeError(f"aqlm_b200: {msg}")
+
+
+def reload_tunables() -> None:
+    """Re-read the AQLM_B200_* experiment switches after changing os.environ (they are cached per process)."""
+    lib().aqlm_b200_reload_tunables()
 
 
 def launch_count() -> int:

@@ -17,10 +17,10 @@ namespace aqlm_b200 {
 std::atomic<uint64_t> g_launch_count{0};
 
 const DeviceInfo* device_info() {
-  static DeviceInfo infos[64];
+  static DeviceInfo infos[kMaxDevices];
   static std::mutex mu;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
     fail(AQLM_B200_ERR_CUDA, "cudaGetDevice failed (no CUDA device / driver?)");
     return nullptr;
   }
@@ -36,6 +36,7 @@ const DeviceInfo* device_info() {
         fail(AQLM_B200_ERR_CUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
         return nullptr;
       }
+      d.index = dev;
       d.ok = true;
     }
   }
@@ -49,6 +50,37 @@ const DeviceInfo* device_info() {
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
+}
+
+// Experiment switches (environment variables), read ONCE per process -- not per launch -- and again only when a tool
+// calls aqlm_b200_reload_tunables() after changing the environment.  Defaults are the shipped configuration.
+struct Tunables {
+  int pdl, gemv_ctas_per_sm, gemv_threads, gather_mode, gemv_v2, force_generic;
+  int disable_lut, lut_ctas_per_sm, lut_debug;
+  int disable_tcgen05, gemm_stages, gemm_ksplit, gemm_cluster, gemm_debug, gemm_gather_mode, gemm_v2, gemm_tile_m;
+  void load() {
+    pdl = env_int("AQLM_B200_PDL", 1);
+    gemv_ctas_per_sm = env_int("AQLM_B200_GEMV_CTAS_PER_SM", 1);
+    gemv_threads = env_int("AQLM_B200_GEMV_THREADS", kGemv1x16Threads);
+    gather_mode = env_int("AQLM_B200_GATHER_MODE", 0);
+    gemv_v2 = env_int("AQLM_B200_GEMV_V2", 1);
+    force_generic = env_int("AQLM_B200_FORCE_GENERIC", 0);
+    disable_lut = env_int("AQLM_B200_DISABLE_LUT", 0);
+    lut_ctas_per_sm = env_int("AQLM_B200_LUT_CTAS_PER_SM", 2);  // 128 regs x 256 threads: registers allow 2
+    lut_debug = env_int("AQLM_B200_LUT_DEBUG", 0);
+    disable_tcgen05 = env_int("AQLM_B200_DISABLE_TCGEN05", 0);
+    gemm_stages = env_int("AQLM_B200_GEMM_STAGES", 0);
+    gemm_ksplit = env_int("AQLM_B200_GEMM_KSPLIT", 0);
+    gemm_cluster = env_int("AQLM_B200_GEMM_CLUSTER", 1);  // measured: no gain, kept for experiments
+    gemm_debug = env_int("AQLM_B200_GEMM_DEBUG", 0);
+    gemm_gather_mode = env_int("AQLM_B200_GEMM_GATHER_MODE", 1);  // ld.global.cg: do not allocate gather lines in the small L1
+    gemm_v2 = env_int("AQLM_B200_GEMM_V2", -1);                   // -1: per-scheme default
+    gemm_tile_m = env_int("AQLM_B200_GEMM_TILE_M", 0);            // 0: chosen by the plan
+  }
+};
+static Tunables& tun() {
+  static Tunables t = [] { Tunables x; x.load(); return x; }();
+  return t;
 }
 
 static int validate(const aqlm_b200_weight_t* w, bool need_scales) {
@@ -78,9 +110,18 @@ static int validate(const aqlm_b200_weight_t* w, bool need_scales) {
   return AQLM_B200_OK;
 }
 
+// Opt-in dynamic shared memory.  cudaFuncSetAttribute applies to the CURRENT device only, so the high-water mark is
+// kept per (kernel instantiation, device): a process that drives several GPUs configures each of them.
+struct SmemMarks {
+  std::atomic<size_t> v[kMaxDevices];
+};
 template <typename KernelT>
-static int set_smem(KernelT kernel, size_t smem) {
-  if (smem > 48 * 1024) AQLM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+static int ensure_smem(KernelT kernel, size_t smem, SmemMarks& marks, const DeviceInfo* di) {
+  std::atomic<size_t>& m = marks.v[di->index];
+  if (smem > 48 * 1024 && m.load(std::memory_order_relaxed) < smem) {
+    AQLM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    m.store(smem, std::memory_order_relaxed);
+  }
   return AQLM_B200_OK;
 }
 
@@ -97,15 +138,11 @@ static size_t vec_smem_bytes(const GemvParams& p, int K, int code_bytes, int G, 
 template <typename T, int K, int CB, int G, int BT, bool CBS, int GM>
 static int launch_vec(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
   constexpr int THREADS = (BT <= 2) ? 1024 : 512;
-  const int grid = di->sm_count * env_int("AQLM_B200_GEMV_CTAS_PER_SM", 1);
+  const int grid = di->sm_count * tun().gemv_ctas_per_sm;
   const size_t smem = vec_smem_bytes(p, K, CB, G, BT, CBS, grid);
   auto kernel = gemv_vec_kernel<T, K, CB, G, BT, CBS, GM, THREADS>;
-  static std::atomic<size_t> configured{0};
-  if (configured.load(std::memory_order_relaxed) < smem) {
-    int rc = set_smem(kernel, smem);
-    if (rc) return rc;
-    configured.store(smem, std::memory_order_relaxed);
-  }
+  static SmemMarks marks;
+  if (int rc = ensure_smem(kernel, smem, marks, di)) return rc;
   // PDL launch: this kernel's weight-only prologue may overlap the previous kernel's tail (see gemv.cuh).
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -114,7 +151,7 @@ static int launch_vec(const GemvParams& p, const DeviceInfo* di, cudaStream_t st
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = env_int("AQLM_B200_PDL", 1) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
@@ -127,12 +164,8 @@ static int launch_1x16_t(const GemvParams& p, const DeviceInfo* di, cudaStream_t
   const int grid = di->sm_count * (512 / THREADS);
   const size_t smem = vec_smem_bytes(p, 1, 2, 8, BT, false, grid);
   auto kernel = gemv_1x16_kernel<T, BT, GM, THREADS>;
-  static std::atomic<size_t> configured{0};
-  if (configured.load(std::memory_order_relaxed) < smem) {
-    int rc = set_smem(kernel, smem);
-    if (rc) return rc;
-    configured.store(smem, std::memory_order_relaxed);
-  }
+  static SmemMarks marks;
+  if (int rc = ensure_smem(kernel, smem, marks, di)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(THREADS);
@@ -140,7 +173,7 @@ static int launch_1x16_t(const GemvParams& p, const DeviceInfo* di, cudaStream_t
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = env_int("AQLM_B200_PDL", 1) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
@@ -152,7 +185,7 @@ static int launch_1x16_t(const GemvParams& p, const DeviceInfo* di, cudaStream_t
 template <typename T, int BT, int GM>
 static int launch_1x16(const GemvParams& p, const DeviceInfo* di, cudaStream_t st) {
   if constexpr (BT == 1 && GM == 0) {
-    if (env_int("AQLM_B200_GEMV_THREADS", kGemv1x16Threads) == 256) return launch_1x16_t<T, BT, GM, 256>(p, di, st);
+    if (tun().gemv_threads == 256) return launch_1x16_t<T, BT, GM, 256>(p, di, st);
   }
   return launch_1x16_t<T, BT, GM, kGemv1x16Threads>(p, di, st);
 }
@@ -173,14 +206,14 @@ static int dispatch_bt(const aqlm_b200_weight_t* w, const GemvParams& p, const D
   const int code_bytes = nbits <= 8 ? 1 : 2;
   const size_t row_bytes = (size_t)p.in_groups * K * code_bytes;
   const bool vec_ok = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(w->codes) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) && !env_int("AQLM_B200_FORCE_GENERIC", 0);
+                      ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) && !tun().force_generic;
   const size_t budget = (size_t)di->max_smem_optin - 1024;
-  const int grid = di->sm_count * env_int("AQLM_B200_GEMV_CTAS_PER_SM", 1);
+  const int grid = di->sm_count * tun().gemv_ctas_per_sm;
   const bool pow2k = (K == 1 || K == 2 || K == 4 || K == 8);
   const size_t need = pow2k ? vec_smem_bytes(p, K, code_bytes, G, BT, nbits == 8, grid) : (size_t)-1;
   if (vec_ok && nbits == 16 && K == 1 && need <= budget) {
-    const int gm = env_int("AQLM_B200_GATHER_MODE", 0);
-    if (G == 8 && env_int("AQLM_B200_GEMV_V2", 1) && vec_smem_bytes(p, 1, 2, 8, BT, false, di->sm_count) <= budget) {
+    const int gm = tun().gather_mode;
+    if (G == 8 && tun().gemv_v2 && vec_smem_bytes(p, 1, 2, 8, BT, false, di->sm_count) <= budget) {
       if (gm == 1) return launch_1x16<T, BT, 1>(p, di, st);
       return launch_1x16<T, BT, 0>(p, di, st);
     }
@@ -277,7 +310,7 @@ static LutPlan lut_plan(const aqlm_b200_weight_t* w, int64_t batch, const Device
   const int K = w->num_codebooks;
   if (batch != 1 || w->nbits_per_codebook != 8 || w->in_group_size != 8) return L;
   if (!(K == 1 || K == 2 || K == 4 || K == 8)) return L;
-  if (env_int("AQLM_B200_DISABLE_LUT", 0)) return L;
+  if (tun().disable_lut) return L;
   if ((reinterpret_cast<uintptr_t>(w->codes) & 7) != 0) return L;
   L.J = (K == 8) ? 16 : 32;
   const int in_groups = (int)(w->in_features / 8);
@@ -285,7 +318,7 @@ static LutPlan lut_plan(const aqlm_b200_weight_t* w, int64_t batch, const Device
   L.smem = (size_t)K * 256 * L.J * 4 + 16;  // LUT + the "last CTA" flag word
   if (L.smem + 1024 > (size_t)di->max_smem_optin) return L;
   int per_sm = (int)((size_t)di->max_smem_optin / (L.smem + 1024));
-  const int want = env_int("AQLM_B200_LUT_CTAS_PER_SM", 2);  // 128 regs x 256 threads: registers allow 2
+  const int want = tun().lut_ctas_per_sm;
   if (per_sm > want) per_sm = want;
   if (per_sm < 1) per_sm = 1;
   // the whole grid must be resident at once (ONE wave): a few CTAs spilling into a second wave double the time
@@ -304,6 +337,8 @@ static LutPlan lut_plan(const aqlm_b200_weight_t* w, int64_t batch, const Device
 template <typename T, int K, int J>
 static int launch_lut(const aqlm_b200_weight_t* w, const void* input, void* output, uint32_t flags, const LutPlan& L,
                       void* workspace, cudaStream_t st) {
+  const DeviceInfo* di = device_info();
+  if (!di) return AQLM_B200_ERR_CUDA;
   LutParams p;
   p.codes = w->codes;
   p.codebooks = w->codebooks;
@@ -320,12 +355,8 @@ static int launch_lut(const aqlm_b200_weight_t* w, const void* input, void* outp
   p.partial_f32 = (flags & AQLM_B200_FLAG_PARTIAL_F32) ? 1 : 0;
   constexpr int THREADS = (K <= 2) ? 256 : 512;  // K >= 4: one CTA per SM (128 KiB LUT), so give it 16 warps
   auto kernel = gemv_lut_kernel<T, K, J, THREADS>;
-  static std::atomic<size_t> configured{0};
-  if (configured.load(std::memory_order_relaxed) < L.smem) {
-    int rc = set_smem(kernel, L.smem);
-    if (rc) return rc;
-    configured.store(L.smem, std::memory_order_relaxed);
-  }
+  static SmemMarks marks;
+  if (int rc = ensure_smem(kernel, L.smem, marks, di)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(L.n_slabs, L.row_blocks);
   cfg.blockDim = dim3(THREADS);
@@ -333,7 +364,7 @@ static int launch_lut(const aqlm_b200_weight_t* w, const void* input, void* outp
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = env_int("AQLM_B200_PDL", 1) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
@@ -385,7 +416,10 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   if (!(K == 1 || K == 2 || K == 4 || K == 8) || 8 * K * cb > kCodeTileBytes) return g;
   if (w->in_features % kGemmBlockK != 0) return g;
   if ((reinterpret_cast<uintptr_t>(w->codes) & 15) != 0) return g;
-  if (env_int("AQLM_B200_DISABLE_TCGEN05", 0)) return g;
+  // TMA needs a 16-byte multiple as the global row stride of the code matrix (1x8: in_features % 128 == 0);
+  // other shapes take the GEMV fallback in aqlm_b200_matmat_dequant_ws
+  if (((size_t)(w->in_features / 8) * K * cb) % 16 != 0) return g;
+  if (tun().disable_tcgen05) return g;
   g.total_kblocks = (int)(w->in_features / kGemmBlockK);
   g.m_tiles = (int)((w->out_features + kGemmBlockM - 1) / kGemmBlockM);
   if (batch <= 256) {
@@ -401,7 +435,7 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   int S = 3;
   while (S > 2 && gemm_smem_layout(S, g.n_tile).total > budget) --S;
   if (gemm_smem_layout(S, g.n_tile).total > budget) return g;
-  const int forced_s = env_int("AQLM_B200_GEMM_STAGES", 0);
+  const int forced_s = tun().gemm_stages;
   if (forced_s >= 2 && forced_s <= S) S = forced_s;
   g.stages = S;
   int ks = 1;
@@ -426,7 +460,7 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
         ks = c;
       }
     }
-    const int forced = env_int("AQLM_B200_GEMM_KSPLIT", 0);
+    const int forced = tun().gemm_ksplit;
     if (forced > 0) ks = forced;
     if (ks > g.total_kblocks) ks = g.total_kblocks;
     if (ks < 1) ks = 1;
@@ -438,7 +472,7 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   g.ksplit = ks;
   // X-tile multicast: CTAs of a cluster (consecutive M tiles, same K range) each TMA-load 1/C of the X tile and
   // multicast it to all C, cutting the L2->SM traffic of X by C.
-  int cl = env_int("AQLM_B200_GEMM_CLUSTER", 1);  // measured: no gain (the limit is per-SM L2->SM ingest), kept for experiments
+  int cl = tun().gemm_cluster;
   while (cl > 1 && (g.m_tiles % cl != 0 || g.n_tile % (8 * cl) != 0)) cl >>= 1;
   g.cluster = cl < 1 ? 1 : cl;
   g.partials_bytes = ks > 1 ? (size_t)g.m_tiles * g.n_tiles * ks * g.n_tile * kGemmBlockM * 4 : 0;
@@ -449,6 +483,8 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
 template <typename T, int K, int CB>
 static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, const GemmPlan& g,
                        void* workspace, cudaStream_t st) {
+  const DeviceInfo* di = device_info();
+  if (!di) return AQLM_B200_ERR_CUDA;
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc) return fail(AQLM_B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   CUtensorMap tx, tc;
@@ -488,20 +524,17 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   p.n_tile = g.n_tile;
   p.stages = g.stages;
   p.cluster = g.cluster;
-  p.debug = env_int("AQLM_B200_GEMM_DEBUG", 0);
-  p.gather_mode = env_int("AQLM_B200_GEMM_GATHER_MODE", 1);  // ld.global.cg: do not allocate gather lines in the small L1
+  p.debug = tun().gemm_debug;
+  p.gather_mode = tun().gemm_gather_mode;
   p.codes = w->codes;
   p.row_bytes = (long long)(w->in_features / 8) * K * CB;
   const size_t smem = gemm_smem_layout(g.stages, g.n_tile).total;
   // producer mapping V2 (one 4-warp group per stage) measured: 1x16 496 vs 505 TFLOP/s (V1), 2x8 134 vs 394, 8x8 196 vs 119
   // -> default only for schemes with many codebooks (profiles/r01/gemm_experiments.md)
-  const bool v2 = env_int("AQLM_B200_GEMM_V2", K >= 4 ? 1 : 0) != 0 && g.stages <= 3 && !(p.debug & 1);
+  const bool v2 = (tun().gemm_v2 < 0 ? (K >= 4 ? 1 : 0) : tun().gemm_v2) != 0 && g.stages <= 3 && !(p.debug & 1);
   auto kernel = v2 ? gemm_dequant_kernel<T, K, CB, true> : gemm_dequant_kernel<T, K, CB, false>;
-  static std::atomic<size_t> configured[2];
-  if (configured[v2].load(std::memory_order_relaxed) < smem) {
-    AQLM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[v2].store(smem, std::memory_order_relaxed);
-  }
+  static SmemMarks marks[2];
+  if (int rc = ensure_smem(kernel, smem, marks[v2 ? 1 : 0], di)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.m_tiles, g.ksplit, g.n_tiles);
   cfg.blockDim = dim3(v2 ? kGemmThreadsV2 : kGemmThreads);
@@ -558,6 +591,7 @@ using namespace aqlm_b200;
 extern "C" {
 
 int aqlm_b200_version(void) { return AQLM_B200_VERSION; }
+void aqlm_b200_reload_tunables(void) { tun().load(); }
 const char* aqlm_b200_last_error(void) { return tls_error_buf(); }
 uint64_t aqlm_b200_launch_count(void) { return g_launch_count.load(); }
 
@@ -820,7 +854,7 @@ int aqlm_b200_allreduce_scale_bias(aqlm_b200_comm* c, const float* partial, cons
   cfg.stream = reinterpret_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = env_int("AQLM_B200_PDL", 1) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (dtype == AQLM_B200_F16) AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, peer_allreduce_epilogue_kernel<__half>, p));

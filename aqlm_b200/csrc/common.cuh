@@ -29,9 +29,11 @@ inline int fail(int status, const char* fmt, ...) {
 #define AQLM_CUDA_CHECK(expr)                                                                                  \
   do {                                                                                                         \
     cudaError_t _e = (expr);                                                                                   \
-    if (_e != cudaSuccess)                                                                                     \
+    if (_e != cudaSuccess) {                                                                                   \
+      (void)cudaGetLastError(); /* clear the sticky-less error so the caller's next launch check is not poisoned */ \
       return ::aqlm_b200::fail(AQLM_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
                                __FILE__, __LINE__);                                                            \
+    }                                                                                                          \
   } while (0)
 
 extern std::atomic<uint64_t> g_launch_count;
@@ -39,7 +41,9 @@ inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relax
 
 // Per-device constants, queried ONCE per device (the reference queries device 0 twice per call,
 // cuda_kernel.cu:486,497).
+constexpr int kMaxDevices = 64;
 struct DeviceInfo {
+  int index = 0;
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   int max_smem_optin = 0;

@@ -330,7 +330,17 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_generic_kernel(const GemvPa
   const int K = p.num_codebooks;
   const int upr = p.in_features >> 3;
   const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
-  const uint4* gx = reinterpret_cast<const uint4*>(p.x);
+  // x may be only element-aligned here (this kernel is also the fallback for a misaligned input): 2-byte loads
+  const uint16_t* gx16 = reinterpret_cast<const uint16_t*>(p.x);
+  auto load_x8 = [&](size_t unit) -> uint4 {
+    const uint16_t* s = gx16 + unit * 8;
+    uint4 v;
+    v.x = (uint32_t)s[0] | ((uint32_t)s[1] << 16);
+    v.y = (uint32_t)s[2] | ((uint32_t)s[3] << 16);
+    v.z = (uint32_t)s[4] | ((uint32_t)s[5] << 16);
+    v.w = (uint32_t)s[6] | ((uint32_t)s[7] << 16);
+    return v;
+  };
   const uint32_t mask = (1u << p.nbits) - 1u;
 
   for (int row = blockIdx.x * kWarps + warp; row < p.out_features; row += gridDim.x * kWarps) {
@@ -357,7 +367,7 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_generic_kernel(const GemvPa
       for (int h = 0; h < UPG; ++h) {
 #pragma unroll
         for (int b = 0; b < BT; ++b)
-          if (b < p.batch) acc[b] = dot8f<T>(wf[h], gx[(size_t)b * upr + j * UPG + h], acc[b]);
+          if (b < p.batch) acc[b] = dot8f<T>(wf[h], load_x8((size_t)b * upr + j * UPG + h), acc[b]);
       }
     }
 #pragma unroll

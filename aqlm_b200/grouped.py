@@ -67,7 +67,10 @@ class QuantizedLinearGroup(nn.Module):
         rows = 1
         for d in input.shape[:-1]:
             rows *= d
-        if not self.fused or not input.is_cuda or rows > 8 or rows < 1:
+        # the fused launch has no autograd node: when a gradient w.r.t. the input is needed (LoRA / PEFT on frozen AQLM
+        # weights), go through the members, whose forward builds one
+        needs_grad = torch.is_grad_enabled() and input.requires_grad
+        if not self.fused or not input.is_cuda or rows > 8 or rows < 1 or needs_grad:
             return tuple(m(input) for m in self.members)
         from .inference_kernels import cuda_kernel
 
@@ -101,7 +104,7 @@ class ShardedQuantizedLinearGroup(nn.Module):
         rows = 1
         for d in input.shape[:-1]:
             rows *= d
-        if not self.fused or not input.is_cuda or rows > 8 or rows < 1:
+        if not self.fused or not input.is_cuda or rows > 8 or rows < 1 or (torch.is_grad_enabled() and input.requires_grad):
             return tuple(m(input) for m in self.members)
         import torch.distributed as dist
 

@@ -101,23 +101,38 @@ class _on_device:
             self.ctx.__exit__(*exc)
 
 
-_WORKSPACES: dict = {}  # (device index, stream handle) -> persistent zero-initialised workspace
+_WORKSPACES: dict = {}   # (device index, stream handle) -> workspace of eager launches on that stream
+_GRAPH_WS: dict = {}     # device index -> workspace baked into CUDA graphs captured on that device
+_RETIRED: list = []      # outgrown buffers are NEVER freed: a captured graph may still hold their address
+_WS_MIN_BYTES = 4 << 20
+
+
+def _grow(table: dict, key, device: torch.device, nbytes: int) -> torch.Tensor:
+    ws = table.get(key)
+    if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _RETIRED.append(ws)
+        ws = torch.zeros(max(nbytes, _WS_MIN_BYTES), dtype=torch.uint8, device=device)
+        table[key] = ws
+    return ws
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Persistent workspace for the split-K GEMM and the LUT GEMV, one per (device, stream): kernels on different streams
-    never share ticket counters or partials.  The kernels leave the counters at zero, so a buffer is zeroed only when it
-    is (re)allocated."""
-    # While a CUDA graph is being captured, use the device-level buffer (key 0 = the default stream's), which the
-    # warm-up call outside the capture allocated from the normal pool: a buffer allocated INSIDE a capture would live in
-    # that graph's private pool and dangle once the graph is destroyed.
-    capturing = torch.cuda.is_current_stream_capturing()
-    key = (device.index, 0 if capturing else _stream_ptr(device))
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.zeros(max(nbytes, 4 << 20), dtype=torch.uint8, device=device)
-        _WORKSPACES[key] = ws
-    return ws
+    """Persistent zero-initialised workspace (ticket counters + fp32 partials) of the split-K GEMM and the LUT GEMV.
+
+    * Eager launches: one buffer per (device, stream), so kernels on different streams never share tickets/partials.
+    * Launches recorded into a CUDA graph: ONE dedicated buffer per device, never shared with eager launches (a replay
+      on a side stream cannot race with default-stream kernels).  It is sized during the eager warm-up calls (every
+      eager request also grows it), so the usual warm-up-then-capture recipe allocates nothing inside the capture; if
+      it must grow inside a capture, the new block comes from that graph's pool and is kept alive here.
+    * Buffers that are outgrown are retired, not freed: graph-baked pointers stay valid and the kernels' "counters are
+      left at zero" invariant holds for every buffer.
+    Graphs that contain workspace-using aqlm_b200 ops must not be replayed concurrently with each other on one device.
+    """
+    if torch.cuda.is_current_stream_capturing():
+        return _grow(_GRAPH_WS, device.index, device, nbytes)
+    _grow(_GRAPH_WS, device.index, device, nbytes)
+    return _grow(_WORKSPACES, (device.index, _stream_ptr(device)), device, nbytes)
 
 
 def _prepare(input, codes, codebooks, scales, bias):

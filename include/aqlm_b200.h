@@ -65,6 +65,9 @@ int aqlm_b200_version(void);
 const char* aqlm_b200_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 uint64_t aqlm_b200_launch_count(void);
+/* The AQLM_B200_* experiment switches (environment variables) are read once per process; tools that change the
+ * environment at run time call this to re-read them.  Not needed in normal use. */
+void aqlm_b200_reload_tunables(void);
 
 /* ---- generic entry points -------------------------------------------------------------------- */
 

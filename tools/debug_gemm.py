@@ -41,5 +41,7 @@ if __name__ == "__main__":
         for k in ("AQLM_B200_GEMM_STAGES", "AQLM_B200_GEMM_KSPLIT", "AQLM_B200_GEMM_DEBUG"):
             os.environ.pop(k, None)
         os.environ.update(env)
+        from aqlm_b200 import _cabi
+        _cabi.reload_tunables()
         run(4096, 14336, 16, reps=3, label=str(env))
         run(4096, 4096, 16, reps=2, label=str(env))

@@ -11,6 +11,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from aqlm_b200 import _cabi  # noqa: E402
 from aqlm_b200.inference_kernels import cuda_kernel  # noqa: E402
 
 L2_BYTES = 126 * 2**20
@@ -83,6 +84,7 @@ def main():
                     for ctas in args.ctas.split(","):
                         os.environ["AQLM_B200_GATHER_MODE"] = mode
                         os.environ["AQLM_B200_GEMV_CTAS_PER_SM"] = ctas
+                        _cabi.reload_tunables()
                         fns = [(lambda w=w: op(x, w[0], w[1], w[2], None)) for w in ws]
                         us = time_graph(fns)
                         gbs = cbytes / us / 1e3
