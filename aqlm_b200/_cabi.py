@@ -43,7 +43,9 @@ def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [HEADER_PATH]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    if os.path.exists(HEADER_PATH):  # absent in a pip-installed copy (the sources include it by relative path)
+        deps.append(HEADER_PATH)
     return any(os.path.getmtime(d) > t for d in deps)
 
 

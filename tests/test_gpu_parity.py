@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 import torch
 from conftest import case_from_meta, golden_cases
-from helpers import TOL_BF16, TOL_FP16_TIGHT, TOL_NORTH_STAR, make_module, oracle_output, to_torch
+from helpers import (TOL_BF16, TOL_FP16_TIGHT, TOL_NORTH_STAR, c_oracle_check, gpu_case, make_module, oracle_output,
+                     to_torch)
 
 from oracle import aqlm_oracle as O
 
@@ -169,11 +170,9 @@ def test_linearity_and_zero_input_at_full_size():
     yb = cuda_kernel.matmat(xb, codes, codebooks, scales, None)
     for i in range(3):
         assert torch.equal(yb[i], cuda_kernel.matmat(xb[i : i + 1], codes, codebooks, scales, None)[0])
-    # gemv against dequant + dense matmul on the GPU (fp32) at full size
-    W = cuda_kernel.dequant(codes, codebooks, scales).float()
-    ref = x1.float() @ W.t()
-    rel = (f(x1) - ref).abs().mean() / ref.abs().mean()
-    assert rel < TOL_FP16_TIGHT
+    # and the full-size result itself against the C oracle (every output row)
+    t = dict(x=x1, codes=codes, codebooks=codebooks, scales=scales, bias=None)
+    assert c_oracle_check(t, f(x1)) < TOL_FP16_TIGHT
 
 
 def test_full_size_config0_matches_oracle_c_port():
@@ -287,19 +286,10 @@ def test_cuda_graph_capture_and_replay():
 
 
 # ---- fused dequant + tcgen05 GEMM (large batch) --------------------------------------------------------------
-def _gpu_ref(x, codes, codebooks, scales, bias):
-    """fp32 reference on the GPU: our dequant kernel (validated against the oracle above) + fp32 matmul."""
-    from aqlm_b200.inference_kernels import cuda_kernel
-
-    W = cuda_kernel.dequant(codes, codebooks, scales).float()
-    y = x.float() @ W.t()
-    return y + bias.float() if bias is not None else y
-
-
 @pytest.mark.parametrize("K,nbits", [(1, 16), (2, 8), (8, 8), (1, 8)])
 @pytest.mark.parametrize("batch", [7, 16, 64, 100, 256, 300])
 def test_tcgen05_gemm_vs_oracle_small(K, nbits, batch):
-    """Sizes the CPU oracle finishes in seconds; in_features % 64 == 0 so the tensor-core kernel is used."""
+    """Sizes the numpy oracle finishes in seconds; in_features % 64 == 0 so the tensor-core kernel is used."""
     from aqlm_b200.inference_kernels import cuda_kernel
 
     case = O.make_case(8000 + K + nbits + batch, 512, 200, K, nbits, 8, batch, bias=(batch % 2 == 0))
@@ -311,40 +301,44 @@ def test_tcgen05_gemm_vs_oracle_small(K, nbits, batch):
 @pytest.mark.parametrize("batch", [16, 64, 256])
 @pytest.mark.parametrize("shape", [(4096, 4096), (4096, 14336), (14336, 4096)])
 def test_tcgen05_gemm_full_size_1x16(shape, batch):
-    """BASELINE configs[3]: Llama-3-8B shapes, bs in {16,64,256}, fp16 operands (parity run)."""
+    """BASELINE configs[3]: Llama-3-8B shapes, bs in {16,64,256}, fp16 operands, against the C ORACLE (row sample that
+    includes both tile edges; every batch row)."""
     from aqlm_b200.inference_kernels import cuda_kernel
 
     fin, fout = shape
-    g = torch.Generator(device=DEV).manual_seed(fin + fout + batch)
-    codes = torch.randint(-32768, 32768, (fout, fin // 8, 1), dtype=torch.int16, device=DEV, generator=g)
-    codebooks = torch.randn((1, 65536, 1, 8), dtype=torch.float16, device=DEV, generator=g)
-    scales = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=DEV, generator=g)).half()
-    x = torch.randn((batch, fin), dtype=torch.float16, device=DEV, generator=g)
-    y = cuda_kernel.matmat_dequant(x, codes, codebooks, scales, None).float()
-    ref = _gpu_ref(x, codes, codebooks, scales, None)
-    rel = ((y - ref).abs().mean() / ref.abs().mean()).item()
+    t = gpu_case(fin, fout, 1, 16, batch, seed=fin + fout + batch)
+    y = cuda_kernel.matmat_dequant(t["x"], t["codes"], t["codebooks"], t["scales"], None)
+    rel = c_oracle_check(t, y)
     assert rel < TOL_FP16_TIGHT, rel
     # deterministic (fixed-order split-K reduction): bitwise identical on a second run
-    y2 = cuda_kernel.matmat_dequant(x, codes, codebooks, scales, None).float()
+    y2 = cuda_kernel.matmat_dequant(t["x"], t["codes"], t["codebooks"], t["scales"], None)
     assert torch.equal(y, y2)
     # gemm op and gemv op agree on the first rows
-    yv = cuda_kernel.matmat(x[:4], codes, codebooks, scales, None).float()
-    assert ((yv - y[:4]).abs().mean() / ref[:4].abs().mean()).item() < 1e-3
+    yv = cuda_kernel.matmat(t["x"][:4], t["codes"], t["codebooks"], t["scales"], None).float()
+    assert ((yv - y[:4].float()).abs().mean() / yv.abs().mean()).item() < 1e-3
 
 
-def test_tcgen05_gemm_bf16_operands():
-    """bf16 operands (the run north_star names): checked against a bf16-fed fp32 reference, bf16 tolerance."""
+@pytest.mark.parametrize("shape", [(4096, 4096), (4096, 14336)])
+def test_tcgen05_gemm_bf16_operands(shape):
+    """bf16 operands (the run north_star names) at BASELINE shapes: C oracle fed with the bf16 values, bf16 tolerance."""
     from aqlm_b200.inference_kernels import cuda_kernel
 
-    fin, fout, batch = 4096, 4096, 256
-    g = torch.Generator(device=DEV).manual_seed(5)
-    codes = torch.randint(-32768, 32768, (fout, fin // 8, 1), dtype=torch.int16, device=DEV, generator=g)
-    codebooks = torch.randn((1, 65536, 1, 8), dtype=torch.bfloat16, device=DEV, generator=g)
-    scales = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=DEV, generator=g)).bfloat16()
-    x = torch.randn((batch, fin), dtype=torch.bfloat16, device=DEV, generator=g)
-    y = cuda_kernel.matmat_dequant(x, codes, codebooks, scales, None).float()
-    ref = _gpu_ref(x, codes, codebooks, scales, None)
-    assert ((y - ref).abs().mean() / ref.abs().mean()).item() < TOL_BF16
+    fin, fout = shape
+    t = gpu_case(fin, fout, 1, 16, 256, dtype=torch.bfloat16, seed=5 + fout)
+    y = cuda_kernel.matmat_dequant(t["x"], t["codes"], t["codebooks"], t["scales"], None)
+    assert c_oracle_check(t, y) < TOL_BF16
+
+
+@pytest.mark.parametrize("K,nbits,shape", [(2, 8, (4096, 11008)), (2, 8, (11008, 4096)), (8, 8, (4096, 4096)),
+                                           (1, 8, (4096, 11008))])
+def test_tcgen05_gemm_full_size_kx8(K, nbits, shape):
+    """BASELINE configs[2] shapes through the large-batch op (Kx8 schemes), against the C oracle."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    fin, fout = shape
+    t = gpu_case(fin, fout, K, nbits, 64, seed=K * 7 + fin, bias=True)
+    y = cuda_kernel.matmat_dequant(t["x"], t["codes"], t["codebooks"], t["scales"], t["bias"])
+    assert c_oracle_check(t, y) < TOL_FP16_TIGHT
 
 
 def test_tcgen05_gemm_without_workspace_matches_split():
@@ -361,30 +355,109 @@ def test_tcgen05_gemm_without_workspace_matches_split():
     assert O.relative_error(y.float().cpu().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
 
 
+def test_gemm_1x8_row_stride_not_tma_compatible_falls_back():
+    """1x8 with in_features % 128 != 0: the code rows are not a 16-byte multiple, so the TMA kernel cannot be used; the
+    large-batch op must still answer (GEMV passes), not fail in cuTensorMapEncodeTiled."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    case = O.make_case(8200, 192, 72, 1, 8, 8, 9, True)
+    t = to_torch(case, DEV)
+    y = cuda_kernel.matmat_dequant(t["x"], t["codes"], t["codebooks"], t["scales"], t["bias"]).float().cpu().numpy()
+    assert O.relative_error(y, oracle_output(case)) < TOL_FP16_TIGHT
+
+
+# ---- full-size matvec parity against the C oracle (every output row) ------------------------------------------------
+LLAMA3_8B = [(4096, 4096), (4096, 1024), (4096, 14336), (14336, 4096)]
+LLAMA3_70B = [(8192, 8192), (8192, 1024), (8192, 28672), (28672, 8192)]
+
+
+@pytest.mark.parametrize("fin,fout", LLAMA3_8B + LLAMA3_70B)
+def test_gemv_1x16_baseline_shapes_vs_c_oracle(fin, fout):
+    """BASELINE configs[1] (Llama-3-8B) and configs[4] (Llama-3-70B, unsharded) 1x16 matvec, all rows, vs the C oracle."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    t = gpu_case(fin, fout, 1, 16, 1, seed=fin * 3 + fout)
+    y = cuda_kernel.matmat(t["x"], t["codes"], t["codebooks"], t["scales"], None)
+    assert c_oracle_check(t, y) < TOL_FP16_TIGHT
+
+
+@pytest.mark.parametrize("batch", [2, 4, 6])
+def test_gemv_1x16_small_batches_full_size(batch):
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    t = gpu_case(4096, 14336, 1, 16, batch, seed=77 + batch, bias=True)
+    y = cuda_kernel.matmat(t["x"], t["codes"], t["codebooks"], t["scales"], t["bias"])
+    assert c_oracle_check(t, y) < TOL_FP16_TIGHT
+
+
+@pytest.mark.parametrize("K,nbits,fin,fout", [(1, 16, 4096, 14336), (1, 16, 14336, 4096), (2, 8, 4096, 11008),
+                                              (8, 8, 4096, 4096), (1, 8, 4096, 11008)])
+def test_gemv_bf16_baseline_shapes_vs_c_oracle(K, nbits, fin, fout):
+    """bf16 GEMV / batch-1 LUT GEMV at BASELINE shapes against a bf16-fed C oracle (all rows)."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    t = gpu_case(fin, fout, K, nbits, 1, dtype=torch.bfloat16, seed=K + fin)
+    y = cuda_kernel.matmat(t["x"], t["codes"], t["codebooks"], t["scales"], None)
+    assert c_oracle_check(t, y) < TOL_BF16
+
+
 # ---- Kx8 dot-product-LUT GEMV (batch 1) -------------------------------------------------------------------------
 @pytest.mark.parametrize("K", [1, 2, 4, 8])
 @pytest.mark.parametrize("fin,fout", [(4096, 4096), (4096, 11008), (11008, 4096), (1032, 77), (264, 33)])
 def test_lut_gemv_kx8(K, fin, fout):
-    """BASELINE configs[2] shapes (Llama-2-7B) plus ragged sizes (in_groups not a multiple of the 32-group slab)."""
+    """BASELINE configs[2] shapes (Llama-2-7B: q/k/v/o, gate/up, down) plus ragged sizes (in_groups not a multiple of the
+    slab), all rows against the C oracle."""
     from aqlm_b200.inference_kernels import cuda_kernel
 
-    g = torch.Generator(device=DEV).manual_seed(K * 1000 + fin + fout)
-    codes = torch.randint(-128, 128, (fout, fin // 8, K), dtype=torch.int8, device=DEV, generator=g)
-    codebooks = torch.randn((K, 256, 1, 8), dtype=torch.float16, device=DEV, generator=g)
-    scales = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=DEV, generator=g)).half()
-    bias = torch.randn((fout,), dtype=torch.float16, device=DEV, generator=g)
-    x = torch.randn((1, fin), dtype=torch.float16, device=DEV, generator=g)
-    y = cuda_kernel.matmat(x, codes, codebooks, scales, bias).float()
-    ref = _gpu_ref(x, codes, codebooks, scales, bias)
-    # the GPU reference rounds W to fp16 (one extra rounding per weight); compare with the fp32-exact oracle budget
-    rel = ((y - ref).abs().mean() / ref.abs().mean()).item()
-    assert rel < TOL_NORTH_STAR / 2, rel
-    y2 = cuda_kernel.matmat(x, codes, codebooks, scales, bias).float()
+    t = gpu_case(fin, fout, K, 8, 1, seed=K * 1000 + fin + fout, bias=True)
+    y = cuda_kernel.matmat(t["x"], t["codes"], t["codebooks"], t["scales"], t["bias"])
+    rel = c_oracle_check(t, y)
+    assert rel < TOL_FP16_TIGHT, rel
+    y2 = cuda_kernel.matmat(t["x"], t["codes"], t["codebooks"], t["scales"], t["bias"])
     assert torch.equal(y, y2)  # fixed-order slab reduction
-    if fin * fout <= 1032 * 77:
-        case = dict(x=x.cpu().numpy(), codes=codes.cpu().numpy(), codebooks=codebooks.cpu().numpy(),
-                    scales=scales.cpu().numpy(), bias=bias.cpu().numpy())
-        assert O.relative_error(y.cpu().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
+
+
+@pytest.mark.parametrize("K,batch", [(2, 2), (2, 5), (8, 3), (1, 6)])
+def test_kx8_small_batches_full_size(K, batch):
+    """Batch 2-6 on 256-entry codebooks (the reference loops its matvec per row, cuda_kernel.cpp:387-421)."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    t = gpu_case(4096, 11008, K, 8, batch, seed=K * 10 + batch)
+    y = cuda_kernel.matmat(t["x"], t["codes"], t["codebooks"], t["scales"], None)
+    assert c_oracle_check(t, y) < TOL_FP16_TIGHT
+
+
+def test_cuda_graph_with_workspace_ops():
+    """Graph capture of the ops that use the persistent workspace (LUT GEMV tickets/partials, split-K GEMM), warmed up on
+    a side stream as in the PyTorch recipe; the workspace later GROWS (bigger eager call) and the graph must still replay
+    correctly (outgrown buffers are retired, never freed)."""
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    t2 = gpu_case(4096, 4096, 2, 8, 1, seed=901)
+    t16 = gpu_case(4096, 4096, 1, 16, 64, seed=902)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            cuda_kernel.matmat(t2["x"], t2["codes"], t2["codebooks"], t2["scales"], None)
+            cuda_kernel.matmat_dequant(t16["x"], t16["codes"], t16["codebooks"], t16["scales"], None)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ya = cuda_kernel.matmat(t2["x"], t2["codes"], t2["codebooks"], t2["scales"], None)
+        yb = cuda_kernel.matmat_dequant(t16["x"], t16["codes"], t16["codebooks"], t16["scales"], None)
+    g.replay()
+    torch.cuda.synchronize()
+    assert c_oracle_check(t2, ya) < TOL_FP16_TIGHT and c_oracle_check(t16, yb) < TOL_FP16_TIGHT
+    # grow the eager workspace well past its initial size, then replay the old graph with new inputs
+    big = gpu_case(4096, 14336, 1, 16, 200, seed=903)
+    cuda_kernel.matmat_dequant(big["x"], big["codes"], big["codebooks"], big["scales"], None)
+    t2["x"].mul_(0.5)
+    t16["x"].mul_(0.5)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert c_oracle_check(t2, ya) < TOL_FP16_TIGHT and c_oracle_check(t16, yb) < TOL_FP16_TIGHT
 
 
 # ---- grouped launch (q/k/v, gate/up) -----------------------------------------------------------------------------
