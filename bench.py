@@ -3,7 +3,7 @@
 
 Contract:
   python bench.py --gpus N --steps K --warmup W        one JSON line on stdout (rank 0)
-  python bench.py --impl reference ...                 the reference's CPU path (oracle port) on host cores
+  python bench.py --impl reference ...                 the reference's OWN CPU code (baseline/_ref, unmodified) on host cores
 
 A "step" is ONE decode-token pass over every quantized linear of the model named in `config.workload`
 (q,k,v,o,gate,up,down x n_layers; batch 1; linears only), each linear with its own codes/codebooks/scales so a step
@@ -158,9 +158,91 @@ def cpu_layer_sample(model, K, nbits, target_seconds, nthreads=0):
                        f"{reps} reps, {kernel}", tok_s=1.0 / (dt * MODELS[model]["layers"]))
 
 
+REF_DIR = os.path.join(REPO, "baseline", "_ref")
+
+
+def import_reference_aqlm():
+    """The UNMODIFIED reference package, pip-installed into the git-ignored baseline/_ref (it travels to the GPU box).
+    Only its CPU path is used here (QuantizedLinear.forward -> dequantize_gemm / numba_gemm_lut); its CUDA extension is
+    never imported in this process."""
+    if not os.path.isdir(os.path.join(REF_DIR, "aqlm")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import aqlm
+
+    if os.path.abspath(REF_DIR) not in os.path.abspath(aqlm.__file__):
+        raise RuntimeError(f"`aqlm` resolved to {aqlm.__file__}, not the reference in {REF_DIR}")
+    return aqlm
+
+
+def cpu_reference_layer_sample(model, K, nbits, target_seconds, numba_threads=1):
+    """Time the reference's own `QuantizedLinear.forward` on CPU (inference_lib/src/aqlm/inference.py:68-75) on ONE decoder
+    layer's 7 linears, bs=1, fp32 (the dtype of benchmark/matmul_benchmark_cpu.py:114-123).  1x16 resolves to
+    `dequantize_gemm` (kernel_selector.py:99-102; torch intra-op threads = all cores); 256-entry codebooks resolve to the
+    Numba LUT kernel (kernel_selector.py:95-98, numba_kernel.py:10-65) with NUMBA_NUM_THREADS=1, the reference benchmark's
+    default (`--nthreads 1`) and the only race-free setting.  Returns None when baseline/_ref is absent."""
+    lut = 2**nbits == 256
+    if lut:
+        os.environ.setdefault("NUMBA_NUM_THREADS", str(numba_threads))
+    try:
+        aqlm = import_reference_aqlm()
+    except Exception as e:
+        print(f"[bench] reference package unusable ({type(e).__name__}: {e}); falling back to the oracle port", file=sys.stderr)
+        return None
+    if aqlm is None:
+        return None
+    import torch
+
+    torch.manual_seed(0)
+    lo, hi = (-128, 128) if nbits <= 8 else (-(2 ** (nbits - 1)), 2 ** (nbits - 1))
+    mods = []
+    for _, fin, fout in layer_linears(model):
+        m = aqlm.QuantizedLinear(fin, fout, 8, 1, K, nbits, bias=False, dtype=torch.float32)
+        m.codes.data = torch.randint(lo, hi, m.codes.shape, dtype=m.codes.dtype)
+        m.codebooks.data = torch.randn(m.codebooks.shape)
+        m.scales.data = torch.randn(m.scales.shape)
+        mods.append((m, torch.randn(1, fin)))
+    nbytes = sum(code_bytes(fin, fout, K, nbits) for _, fin, fout in layer_linears(model))
+
+    def one_pass():
+        with torch.no_grad():
+            for m, x in mods:
+                m(x)
+
+    one_pass()  # warm-up: TorchScript / Numba JIT, the reference's lazy code permutation (inference.py:78-83)
+    t0 = time.perf_counter()
+    one_pass()
+    t1 = time.perf_counter() - t0
+    reps = max(1, min(50, int(target_seconds / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_pass()
+    dt = (time.perf_counter() - t0) / reps
+    cores = numba_threads if lut else torch.get_num_threads()
+    kernel = ("aqlm.inference_kernels.numba_kernel.numba_gemm_lut (baseline/_ref, NUMBA_NUM_THREADS=%d)" % numba_threads) if lut \
+        else "aqlm.inference_kernels.dequantization.dequantize_gemm (baseline/_ref, torch CPU ops)"
+    return dict(value=nbytes / dt / 1e9, unit="GB/s", cores=cores, kind="reference", seconds_per_layer=dt,
+                sample=f"one decoder layer (7 linears, {nbytes / 2**20:.1f} MiB of codes) of {model} {K}x{nbits}, bs=1, fp32, "
+                       f"{reps} reps through the reference's own QuantizedLinear.forward on CPU: {kernel}",
+                tok_s=1.0 / (dt * MODELS[model]["layers"]))
+
+
+def cpu_baseline_sample(model, K, nbits, target_seconds):
+    """cpu_baseline object: the reference's own CPU code when baseline/_ref is present (kind "reference"), with the
+    oracle's C port (all cores) reported beside it; the port alone (kind "port") otherwise."""
+    ref = cpu_reference_layer_sample(model, K, nbits, target_seconds)
+    port = cpu_layer_sample(model, K, nbits, target_seconds=min(target_seconds, 8.0))
+    if ref is None:
+        return port
+    ref["port"] = {k: port[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    return ref
+
+
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU implementation of the path (oracle port; the Python reference cannot
-    travel to the GPU box), all host threads, bounded sample per step = one decoder layer."""
+    """`--impl reference`: the reference's own CPU implementation of the path -- the UNMODIFIED package in baseline/_ref,
+    through its public module API (`aqlm.QuantizedLinear.forward` on CPU tensors) -- on the box's host cores; a bounded
+    sample per step = one decoder layer.  Falls back to the oracle port only when baseline/_ref is not installed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -168,9 +250,12 @@ def run_reference(args):
     model = args.workload or ("llama3-8b" if args.gpus == 1 else "llama3-70b")
     steps = max(1, args.steps)
     budget = 150.0  # seconds for all steps
-    base = cpu_layer_sample(model, K, nbits, target_seconds=min(20.0, budget / 4))
+    base = cpu_baseline_sample(model, K, nbits, target_seconds=min(20.0, budget / 4))
     per = base["seconds_per_layer"]
     steps_run = max(1, min(steps, int(budget / max(per, 1e-6))))
+    cpu = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if "port" in base:
+        cpu["port"] = base["port"]
     line = {
         "impl": "reference", "metric": "aqlm_matvec_code_GBps", "value": base["value"], "unit": "GB/s",
         "n_gpus": args.gpus, "steps": steps_run, "warmup": args.warmup, "ms_per_step": per * 1e3,
@@ -178,7 +263,7 @@ def run_reference(args):
         "tok_s_linears_only": base["tok_s"],
         "config": {"workload": f"{model} {K}x{nbits} g8 all-linear matvec sweep, bs=1",
                    "step": "bounded sample: ONE decoder layer (7 linears) per step on host cores"},
-        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": cpu,
         "e2e": {"value": base["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -233,9 +318,123 @@ def group_layers(layers, K, nbits, world):
     return out
 
 
-def secondary_metrics(device, peak_hbm):
-    """Short extra measurements reported beside the headline (not part of `value`): the batch-256 fused dequant+tcgen05
-    GEMM (BASELINE configs[3]) and the Kx8 LUT matvec (configs[2]).  CUDA-graph replay over rotating weight copies."""
+def sharded_parity(model, K, nbits, device, rank, world, peer_comm):
+    """Driver-visible correctness of the multi-GPU data path (run before timing, N > 1): every distinct linear shape of the
+    workload goes once through the sharded path -- the fused peer-memory exchange AND the NCCL all-reduce variant, plus the
+    grouped q/k/v and gate/up launches the timed step uses -- and is compared with the UNSHARDED single-GPU module on the
+    same full tensors (metric of matmul_benchmark.py:108); one shape is also checked against the C oracle (rank 0).
+    Every rank builds identical full tensors from a shared seed and keeps its in_features slice."""
+    import torch
+    import torch.distributed as dist
+
+    import aqlm_b200
+    from aqlm_b200.grouped import ShardedQuantizedLinearGroup
+    from aqlm_b200.sharded import ShardedQuantizedLinear
+
+    lo, hi = (-128, 128) if nbits <= 8 else (-(2 ** (nbits - 1)), 2 ** (nbits - 1))
+    lin = {name: (fin, fout) for name, fin, fout in layer_linears(model)}
+
+    def full(fin, fout, seed):
+        g = torch.Generator(device=device).manual_seed(seed)
+        return dict(codes=torch.randint(lo, hi, (fout, fin // 8, K), dtype=torch.int8 if nbits <= 8 else torch.int16,
+                                        device=device, generator=g),
+                    codebooks=torch.randn((K, 2**nbits, 1, 8), dtype=torch.float16, device=device, generator=g),
+                    scales=(0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=device, generator=g)).half(),
+                    x=torch.randn((1, fin), dtype=torch.float16, device=device, generator=g))
+
+    def unsharded(t):
+        m = aqlm_b200.QuantizedLinear(t["codes"].shape[1] * 8, t["codes"].shape[0], 8, 1, K, nbits, bias=False, device=device,
+                                      dtype=torch.float16)
+        m.codes.data, m.codebooks.data, m.scales.data = t["codes"], t["codebooks"], t["scales"]
+        return m(t["x"]).float()
+
+    def rel(y, ref):
+        return float(((y.float() - ref).abs().mean() / ref.abs().mean()).item())
+
+    worst, shapes, oracle_rel = 0.0, [], None
+    distinct = sorted({v for v in lin.values()})
+    for i, (fin, fout) in enumerate(distinct):
+        t = full(fin, fout, 4242 + i)
+        ref = unsharded(t)
+        for kind, comm in (("peer", peer_comm), ("nccl", None)):
+            if kind == "peer" and comm is None:
+                continue
+            m = ShardedQuantizedLinear.from_full(t["codes"], t["codebooks"], t["scales"], None, rank=rank, world_size=world,
+                                                 peer_comm=comm)
+            for _ in range(2):  # second call exercises the step counter / buffer-set alternation
+                y = m(t["x"])
+            e = rel(y, ref)
+            worst = max(worst, e)
+            shapes.append({"shape": f"{fin}x{fout}", "exchange": kind, "rel": e})
+            del m
+        if i == 0 and rank == 0:
+            try:
+                from oracle import c_oracle
+
+                f32 = lambda a: a.float().cpu().numpy()  # noqa: E731
+                yo = c_oracle.dequantize_gemm(f32(t["x"]), t["codes"].cpu().numpy(), f32(t["codebooks"]), f32(t["scales"]), None)
+                oracle_rel = rel(y, torch.from_numpy(yo).to(device))
+                worst = max(worst, oracle_rel)
+            except Exception as e:  # the checker must not take the bench down; its absence is reported
+                oracle_rel = f"unavailable: {type(e).__name__}: {e}"
+        del t, ref
+    if (K, nbits) == (1, 16):
+        for names in (("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")):
+            ts = [full(*lin[n], 5151 + j) for j, n in enumerate(names)]
+            for t in ts[1:]:
+                t["x"] = ts[0]["x"]
+            refs = [unsharded(t) for t in ts]
+            ms = [ShardedQuantizedLinear.from_full(t["codes"], t["codebooks"], t["scales"], None, rank=rank, world_size=world,
+                                                   peer_comm=peer_comm) for t in ts]
+            grp = ShardedQuantizedLinearGroup(ms)
+            for _ in range(2):
+                ys = grp(ts[0]["x"])
+            for n, y, ref in zip(names, ys, refs):
+                e = rel(y, ref)
+                worst = max(worst, e)
+                shapes.append({"shape": f"{lin[n][0]}x{lin[n][1]}", "exchange": "grouped " + ("peer" if peer_comm is not None else "nccl"),
+                               "rel": e})
+            del ts, refs, ms, grp
+    torch.cuda.synchronize()
+    w = torch.tensor([worst], device=device)
+    dist.all_reduce(w, op=dist.ReduceOp.MAX)  # a rank that saw a wrong result fails everyone
+    torch.cuda.empty_cache()
+    return {"max_rel": float(w.item()), "tolerance": 1e-3, "vs": "unsharded single-GPU aqlm_b200.QuantizedLinear on the same full tensors",
+            "c_oracle_rel_first_shape": oracle_rel, "shapes": shapes}
+
+
+def _json_lines(text):
+    rows = []
+    for ln in text.splitlines():
+        ln = ln.strip()
+        if ln.startswith("{"):
+            try:
+                rows.append(json.loads(ln))
+            except Exception:
+                pass
+    return rows
+
+
+def _tool(argv, timeout):
+    """Run a tools/ script in its own process (the reference and aqlm_b200 both register `aqlm::` ops) and parse its
+    JSON lines; errors are reported, never raised."""
+    try:
+        r = subprocess.run([sys.executable, *argv], capture_output=True, text=True, timeout=timeout, cwd=REPO)
+        rows = _json_lines(r.stdout)
+        if r.returncode != 0 and not rows:
+            return {"error": f"exit {r.returncode}: {r.stderr[-400:]}"}
+        return rows
+    except subprocess.TimeoutExpired:
+        return {"error": f"timeout after {timeout}s"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def secondary_metrics(device, peak_hbm, args):
+    """Extra measurements reported beside the headline (not part of `value`): the fused dequant + tcgen05 GEMM (BASELINE
+    configs[3]), the Kx8 matvec on every Llama-2-7B shape (configs[2]), the other schemes of SURVEY §8 f4 (1x8, 1x16 g=16,
+    bf16), the reference's own CUDA kernels and Numba CPU kernel timed in the same job, and HF `generate` tok/s (§8 f1).
+    Matvec/GEMM numbers: CUDA-graph replay over rotating weight copies (codes come from HBM), CUDA events."""
     import torch
 
     from aqlm_b200.inference_kernels import cuda_kernel
@@ -265,38 +464,82 @@ def secondary_metrics(device, peak_hbm):
         torch.cuda.synchronize()
         return a.elapsed_time(b) * 1e3 / iters / len(fns)  # us per call
 
-    def weights(fin, fout, K, nbits, copies, dt):
+    def weights(fin, fout, K, nbits, copies, dt, g=8):
         ws = []
         for _ in range(copies):
             lo, hi = (-128, 128) if nbits <= 8 else (-32768, 32768)
-            codes = torch.randint(lo, hi, (fout, fin // 8, K), dtype=torch.int8 if nbits <= 8 else torch.int16, device=device)
-            cb = torch.randn((K, 2**nbits, 1, 8), dtype=dt, device=device)
+            codes = torch.randint(lo, hi, (fout, fin // g, K), dtype=torch.int8 if nbits <= 8 else torch.int16, device=device)
+            cb = torch.randn((K, 2**nbits, 1, g), dtype=dt, device=device)
             sc = (0.75 + 0.5 * torch.rand((fout, 1, 1, 1), device=device)).to(dt)
             ws.append((codes, cb, sc))
         return ws
 
-    out = {"gemm": [], "kx8_matvec": []}
-    fin, fout = 4096, 14336
-    for dt, name in ((torch.float16, "f16"), (torch.bfloat16, "bf16")):
-        ws = weights(fin, fout, 1, 16, 12, dt)
-        for bs in (16, 64, 256):
-            x = torch.randn((bs, fin), dtype=dt, device=device)
-            us = timed([(lambda w=w: cuda_kernel.matmat_dequant(x, w[0], w[1], w[2], None)) for w in ws])
-            tf = 2.0 * bs * fin * fout / us / 1e6
-            out["gemm"].append({"shape": f"{fin}x{fout}", "scheme": "1x16", "batch": bs, "operands": name, "us": round(us, 2),
-                                "tflops": round(tf, 1), "frac_of_measured_bf16_peak": round(tf / tpeak, 4)})
-        del ws
-    for K, nbits, shape in ((2, 8, (4096, 11008)), (8, 8, (4096, 11008)), (2, 8, (4096, 4096))):
-        fin, fout = shape
+    out = {"gemm": [], "kx8_matvec": [], "other_schemes_matvec": []}
+    for fin, fout in ((4096, 14336), (4096, 4096)):
+        for dt, name in ((torch.float16, "f16"), (torch.bfloat16, "bf16")):
+            if (fin, fout) == (4096, 4096) and name == "f16":
+                continue
+            ws = weights(fin, fout, 1, 16, 12 if fout > 4096 else 32, dt)
+            for bs in ((16, 64, 256) if fout > 4096 else (256,)):
+                x = torch.randn((bs, fin), dtype=dt, device=device)
+                us = timed([(lambda w=w: cuda_kernel.matmat_dequant(x, w[0], w[1], w[2], None)) for w in ws])
+                tf = 2.0 * bs * fin * fout / us / 1e6
+                out["gemm"].append({"shape": f"{fin}x{fout}", "scheme": "1x16", "batch": bs, "operands": name, "us": round(us, 2),
+                                    "tflops": round(tf, 1), "frac_of_measured_bf16_peak": round(tf / tpeak, 4)})
+            del ws
+    # backward op (fused dequant-transpose GEMM): grad_in[bs, in] = (grad_out * scales) @ W
+    try:
+        ws = weights(4096, 14336, 1, 16, 12, torch.float16)
+        go = torch.randn((256, 14336), dtype=torch.float16, device=device)
+        us = timed([(lambda w=w: cuda_kernel.matmat_dequant_transposed(go, w[0], w[1], w[2], None)) for w in ws])
+        tf = 2.0 * 256 * 4096 * 14336 / us / 1e6
+        out["gemm_transposed"] = [{"shape": "14336->4096 (W 4096x14336)", "scheme": "1x16", "batch": 256, "us": round(us, 2),
+                                   "tflops": round(tf, 1), "frac_of_measured_bf16_peak": round(tf / tpeak, 4)}]
+        del ws, go
+    except Exception as e:
+        out["gemm_transposed"] = {"error": f"{type(e).__name__}: {e}"}
+    kx8 = [(2, (4096, 11008)), (2, (11008, 4096)), (2, (4096, 4096)), (8, (4096, 11008)), (8, (11008, 4096)), (8, (4096, 4096)),
+           (1, (4096, 11008))]
+    for K, (fin, fout) in kx8:
         cb = fout * (fin // 8) * K
-        ws = weights(fin, fout, K, nbits, max(2, min(40, 300 * 2**20 // cb)), torch.float16)
+        ws = weights(fin, fout, K, 8, max(2, min(40, 300 * 2**20 // cb)), torch.float16)
         x = torch.randn((1, fin), dtype=torch.float16, device=device)
         us = timed([(lambda w=w: cuda_kernel.matmat(x, w[0], w[1], w[2], None)) for w in ws])
-        out["kx8_matvec"].append({"shape": f"{fin}x{fout}", "scheme": f"{K}x{nbits}", "us": round(us, 2),
+        out["kx8_matvec"].append({"shape": f"{fin}x{fout}", "scheme": f"{K}x8", "us": round(us, 2),
                                   "code_GBps": round(cb / us / 1e3, 1), "frac_of_hbm_peak": round(cb / us / 1e3 / peak_hbm, 4)})
+        del ws
+    for label, K, nbits, g, dt, (fin, fout) in (("1x16 g16 f16", 1, 16, 16, torch.float16, (4096, 14336)),
+                                                ("1x16 g8 bf16", 1, 16, 8, torch.bfloat16, (4096, 14336)),
+                                                ("2x8 g8 bf16", 2, 8, 8, torch.bfloat16, (4096, 11008))):
+        cb = fout * (fin // g) * K * (2 if nbits > 8 else 1)
+        ws = weights(fin, fout, K, nbits, max(2, min(40, 300 * 2**20 // cb)), dt, g)
+        x = torch.randn((1, fin), dtype=dt, device=device)
+        us = timed([(lambda w=w: cuda_kernel.matmat(x, w[0], w[1], w[2], None)) for w in ws])
+        out["other_schemes_matvec"].append({"case": label, "shape": f"{fin}x{fout}", "us": round(us, 2),
+                                            "code_GBps": round(cb / us / 1e3, 1),
+                                            "frac_of_hbm_peak": round(cb / us / 1e3 / peak_hbm, 4)})
         del ws
     out["tensor_peak_tflops"] = tpeak
     torch.cuda.empty_cache()
+    if not args.skip_reference_gpu and os.path.isdir(os.path.join(REF_DIR, "aqlm")):
+        # the reference's stock CUDA kernels (baseline/_ref, JIT-built for sm_100) with the same timing protocol
+        out["reference_gpu"] = _tool([os.path.join("tools", "compare_reference_gpu.py"), "--cases", "quick"], timeout=420)
+        out["generate"] = {
+            "ours_fused": _tool([os.path.join("tools", "generate_benchmark.py"), "--impl", "ours", "--fuse", "--output_length", "64",
+                                 "--benchmark_iters", "2"], timeout=300),
+            "ours": _tool([os.path.join("tools", "generate_benchmark.py"), "--impl", "ours", "--output_length", "64",
+                           "--benchmark_iters", "2"], timeout=300),
+            "reference": _tool([os.path.join("tools", "generate_benchmark.py"), "--impl", "reference", "--output_length", "64",
+                                "--benchmark_iters", "2"], timeout=420),
+        }
+    if not args.skip_cpu:
+        # the reference's Numba LUT kernel (benchmark/matmul_benchmark_cpu.py times this algorithm) on one Llama-2-7B layer, 2x8
+        try:
+            ref = cpu_reference_layer_sample("llama2-7b", 2, 8, target_seconds=6.0)
+            if ref is not None:
+                out["reference_cpu_numba_2x8"] = {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:
+            out["reference_cpu_numba_2x8"] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 
@@ -333,6 +576,15 @@ def run_ours(args):
             except Exception as e:
                 print(f"[bench] peer-memory communicator unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
                 peer_comm = None
+    parity = None
+    if world > 1 and not args.skip_parity:
+        parity = sharded_parity(model, K, nbits, device, rank, world, peer_comm)
+        if parity["max_rel"] > parity["tolerance"]:
+            if rank == 0:
+                print(json.dumps({"error": "sharded_parity failed", "sharded_parity": parity}), flush=True)
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(3)
     layers = build_model(model, K, nbits, n_layers, device, rank, world, peer_comm)
     grouped = not args.no_group and (K, nbits) == (1, 16)
     if grouped:
@@ -412,11 +664,14 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     clocks = sampler.stop() if sampler else None
 
-    # single-GPU reference point for the SAME workload when N > 1 (rank 0, unsharded, reduced layer count if needed)
+    # single-GPU point of the SAME workload when N > 1: rank 0 alone, unsharded, same grouping, FULL depth (Llama-3-70B
+    # 1x16 is 16 GiB of codes: fits beside the shard), so the driver's curve can be read as same-workload strong scaling
     same_n1 = None
     if world > 1 and rank == 0 and not args.skip_n1:
         try:
-            l1 = build_model(model, K, nbits, min(n_layers, 16), device, 0, 1)
+            l1 = build_model(model, K, nbits, n_layers, device, 0, 1)
+            if grouped:
+                l1 = group_layers(l1, K, nbits, 1)
             xs = {n: torch.randn((1, n), dtype=torch.float16, device=device) for n in {n for mods in l1 for _, n in mods}}
 
             def s1():
@@ -436,10 +691,11 @@ def run_ours(args):
                 g1.replay()
             b.record()
             torch.cuda.synchronize()
-            bytes1 = model_code_bytes(model, K, nbits, min(n_layers, 16))
-            same_n1 = {"value": bytes1 / (a.elapsed_time(b) / 5 * 1e-3) / 1e9, "unit": "GB/s",
-                       "note": f"rank 0 alone, unsharded, {min(n_layers, 16)} layers of the same model"}
-            del l1, g1
+            v1 = total_bytes / (a.elapsed_time(b) / 5 * 1e-3) / 1e9
+            same_n1 = {"value": v1, "unit": "GB/s",
+                       "note": f"rank 0 alone, unsharded, {n_layers} layers, {'grouped' if grouped else 'ungrouped'} launches"}
+            del l1, g1, xs
+            torch.cuda.empty_cache()
         except Exception as e:
             same_n1 = {"error": f"{type(e).__name__}: {e}"}
     if world > 1:
@@ -454,8 +710,10 @@ def run_ours(args):
         achieved = per_gpu_bytes / n_lin / (avg_launch_us * 1e-6) / 1e9
         cpu = None
         if world == 1 and not args.skip_cpu:
-            cpu = cpu_layer_sample(model, K, nbits, target_seconds=15.0)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu_full = cpu_baseline_sample(model, K, nbits, target_seconds=15.0)
+            cpu = {k: cpu_full[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            if "port" in cpu_full:
+                cpu["port"] = cpu_full["port"]
         traffic = None
         tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
@@ -489,27 +747,43 @@ def run_ours(args):
             try:
                 del layers, graph
                 torch.cuda.empty_cache()
-                line["secondary"] = secondary_metrics(device, peak)
+                line["secondary"] = secondary_metrics(device, peak, args)
             except Exception as e:  # never lose the headline line to a secondary measurement
                 line["secondary"] = {"error": f"{type(e).__name__}: {e}"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if same_n1 is not None:
             line["same_workload_single_gpu"] = same_n1
+            if "value" in same_n1:
+                line["same_workload_scaling_efficiency"] = value / (world * same_n1["value"])
+        if parity is not None:
+            line["sharded_parity"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
-        # Tear down without touching the NCCL communicator: destroying it while CUDA graphs that captured NCCL kernels
-        # are alive hung for the watchdog's full timeout on this stack (profiles/r01/README.md).  Everything is already
-        # synchronised and printed; leave through os._exit so no destructor runs.
+        # Clean teardown: drop the CUDA graphs (they may hold captured NCCL kernels), sync, then destroy the process group.
+        # A watchdog leaves through os._exit if the destroy does not return (seen in round 1 with graphs that captured
+        # NCCL all-reduces still alive); everything has been printed and synchronised by then.
         try:
-            del graph
+            if graph is not None:
+                graph.reset()
         except Exception:
             pass
+        graph = None
+        layers = None
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+
+        def _bail():
+            print("[bench] destroy_process_group did not return within 20 s; leaving through os._exit", file=sys.stderr, flush=True)
+            os._exit(0)
+
+        wd = threading.Timer(20.0, _bail)
+        wd.daemon = True
+        wd.start()
+        dist.destroy_process_group()
+        wd.cancel()
 
 
 def main():
@@ -526,6 +800,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-n1", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true", help="N>1: skip the sharded-vs-unsharded correctness pass")
+    ap.add_argument("--skip-reference-gpu", action="store_true", help="skip the reference CUDA kernels / generate legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -42,6 +42,7 @@ def time_graph(fn_list, iters=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
+    ap.add_argument("--cases", default="all", choices=["all", "quick"], help="quick: the subset bench.py reports in `secondary`")
     args = ap.parse_args()
     import aqlm  # the reference
     assert "baseline/_ref" in aqlm.__file__, aqlm.__file__
@@ -52,6 +53,9 @@ def main():
     cases = [("1x16", 1, 16, (4096, 4096), 1), ("1x16", 1, 16, (4096, 14336), 1), ("1x16", 1, 16, (14336, 4096), 1),
              ("2x8", 2, 8, (4096, 4096), 1), ("2x8", 2, 8, (4096, 11008), 1),
              ("1x16", 1, 16, (4096, 14336), 256), ("1x16", 1, 16, (4096, 14336), 64), ("1x16", 1, 16, (4096, 4096), 256)]
+    if args.cases == "quick":
+        cases = [("1x16", 1, 16, (4096, 4096), 1), ("1x16", 1, 16, (4096, 14336), 1), ("2x8", 2, 8, (4096, 11008), 1),
+                 ("1x16", 1, 16, (4096, 14336), 256), ("1x16", 1, 16, (4096, 4096), 256)]
     for scheme, K, nbits, (fin, fout), bs in cases:
         cbytes = fout * (fin // 8) * K * ((nbits + 7) // 8)
         copies = max(2, min(64, (2 * L2_BYTES + cbytes - 1) // cbytes + 1))

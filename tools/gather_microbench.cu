@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <string>
 #include <vector>
 
 #define CK(x)                                                                                   \
@@ -246,6 +247,21 @@ int main(int argc, char** argv) {
   };
 #define BUF(i) (codes + (size_t)((i) % NBUF) * nchunks)
 
+  if (argc > 1 && std::string(argv[1]) == "ncu") {
+    // One launch of each representative variant, for `ncu --set full` (names the unit behind the gather cap):
+    // best LDG variant, the 2-chunk variant, pure shared-memory gathers and the smem/global hybrid.
+    CK(cudaFuncSetAttribute(k_lds<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
+    CK(cudaFuncSetAttribute(k_hybrid<12288, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 16));
+    for (int i = 0; i < 2; ++i) {
+      k_ldg<0, 1><<<sms * 4, 256>>>(BUF(i), nchunks, table, out);
+      k_ldg<1, 1><<<sms * 4, 256>>>(BUF(i), nchunks, table, out);
+      k_ldg<0, 2><<<sms * 4, 256>>>(BUF(i), nchunks, table, out);
+      k_lds<13><<<sms, 1024, 8192 * 16>>>(BUF(i), nchunks, table, out);
+      k_hybrid<12288, 0><<<sms, 1024, 12288 * 16>>>(BUF(i), nchunks, table, out);
+    }
+    CK(cudaDeviceSynchronize());
+    return 0;
+  }
   report("stream_only", 8, 256, time_ms([&](int i) { k_stream<<<sms * 8, 256>>>(BUF(i), nchunks, out); }, iters));
 
   const int cfgs[][2] = {{2, 256}, {4, 256}, {8, 256}, {2, 1024}, {1, 1024}};
