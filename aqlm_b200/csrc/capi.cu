@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "dequant.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_t.cuh"
 #include "gemv.cuh"
 #include "gemv_lut.cuh"
 #include "peer_allreduce.cuh"
@@ -57,7 +58,7 @@ static int env_int(const char* name, int dflt) {
 struct Tunables {
   int pdl, gemv_ctas_per_sm, gemv_threads, gather_mode, gemv_v2, force_generic;
   int disable_lut, lut_ctas_per_sm, lut_debug;
-  int disable_tcgen05, gemm_stages, gemm_ksplit, gemm_cluster, gemm_debug, gemm_gather_mode, gemm_v2, gemm_tile_m;
+  int disable_tcgen05, gemm_stages, gemm_ksplit, gemm_cluster, gemm_debug, gemm_gather_mode, gemm_v2, gemm_tile_m, gemm_atmem;
   void load() {
     pdl = env_int("AQLM_B200_PDL", 1);
     gemv_ctas_per_sm = env_int("AQLM_B200_GEMV_CTAS_PER_SM", 1);
@@ -76,6 +77,7 @@ struct Tunables {
     gemm_gather_mode = env_int("AQLM_B200_GEMM_GATHER_MODE", 1);  // ld.global.cg: do not allocate gather lines in the small L1
     gemm_v2 = env_int("AQLM_B200_GEMM_V2", -1);                   // -1: per-scheme default
     gemm_tile_m = env_int("AQLM_B200_GEMM_TILE_M", 0);            // 0: chosen by the plan
+    gemm_atmem = env_int("AQLM_B200_GEMM_ATMEM", -1);             // A operand in tensor memory; -1: per-scheme default
   }
 };
 static Tunables& tun() {
@@ -405,6 +407,9 @@ constexpr int kGemmMaxTiles = 16384;
 struct GemmPlan {
   bool ok = false;       // tcgen05 path applicable
   int m_tiles = 0, n_tiles = 0, n_tile = 0, ksplit = 1, stages = 0, total_kblocks = 0, cluster = 1;
+  int tile_m = kGemmBlockM;  // output rows per CTA tile
+  bool v2 = false;           // producer mapping: one 4-warp group per stage, thread <-> row
+  bool atmem = false;        // A operand written to tensor memory (needs v2)
   size_t counters_bytes = 0, partials_bytes = 0;
 };
 
@@ -421,7 +426,6 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   if (((size_t)(w->in_features / 8) * K * cb) % 16 != 0) return g;
   if (tun().disable_tcgen05) return g;
   g.total_kblocks = (int)(w->in_features / kGemmBlockK);
-  g.m_tiles = (int)((w->out_features + kGemmBlockM - 1) / kGemmBlockM);
   if (batch <= 256) {
     g.n_tile = (int)((batch + 15) / 16 * 16);
     g.n_tiles = 1;
@@ -429,42 +433,57 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
     g.n_tile = 256;
     g.n_tiles = (int)((batch + 255) / 256);
   }
+  // producer mapping V2 (one 4-warp group per stage) measured: 1x16 496 vs 505 TFLOP/s (V1), 2x8 134 vs 394, 8x8 196 vs 119
+  // -> V2 for schemes with many codebooks; A-in-TMEM builds on V2 (profiles/r01/gemm_experiments.md, profiles/r02/)
+  g.atmem = (tun().gemm_atmem < 0 ? (K == 1) : tun().gemm_atmem != 0) && !(tun().gemm_debug & 1);
+  g.v2 = g.atmem || ((tun().gemm_v2 < 0 ? (K >= 4 ? 1 : 0) : tun().gemm_v2) != 0 && !(tun().gemm_debug & 1));
   const size_t budget = (size_t)di->max_smem_optin;
   // At most 3 stages: shared memory taken here is L1 taken from the codebook gathers (outstanding misses need L1
   // lines); measured at N=256: 4 stages 335 TFLOP/s, 3 stages 484-503, 2 stages 470 (profiles/r01/gemm_experiments.md)
   int S = 3;
-  while (S > 2 && gemm_smem_layout(S, g.n_tile).total > budget) --S;
-  if (gemm_smem_layout(S, g.n_tile).total > budget) return g;
+  while (S > 2 && gemm_smem_layout(S, g.n_tile, g.atmem).total > budget) --S;
+  if (gemm_smem_layout(S, g.n_tile, g.atmem).total > budget) return g;
   const int forced_s = tun().gemm_stages;
   if (forced_s >= 2 && forced_s <= S) S = forced_s;
   g.stages = S;
-  int ks = 1;
-  if (allow_split) {
-    // The kernel is bound by the per-SM codebook-gather rate, so what matters is how many SMs gather.  Model:
-    //   t(ks) = gather_time / sm_efficiency(ks) + split-K fix-up traffic (partials written + read once through L2)
-    //           + waves * fixed per-CTA cost      (checked against a measured sweep, profiles/r01/gemm_experiments.md)
-    const double tiles = (double)g.m_tiles * g.n_tiles;
-    const double gathers = (double)w->out_features * (w->in_features / 8) * K * g.n_tiles;
-    const double t_gather = gathers / 250e9;  // measured chip-wide 16-byte gather rate (profiles/r01/gather_microbench_v1.jsonl)
-    double best = 1e30;
-    const int max_ks = g.total_kblocks / 2 < 16 ? (g.total_kblocks / 2 < 1 ? 1 : g.total_kblocks / 2) : 16;
+  // ---- tile height and split-K: a small cost model over (tile_m, ksplit), in SM clocks ----
+  //   per k-block of one CTA: max(gathers, tensor pipe, shared-memory traffic) + a fixed synchronisation cost;
+  //   per CTA: its k-blocks + a fixed cost (launch ramp, TMEM alloc, pipeline fill, epilogue: ~5 us measured);
+  //   per launch: waves x CTA time + split-K fix-up traffic (partials written and read once through L2).
+  // The gather rate is the measured per-SM rate of random 16-byte codebook reads (profiles/: ~0.85/clk from L2 for the
+  // 1 MiB 1x16 codebook; 256-entry codebooks are L1-resident and gather faster).
+  const double clk = 1.9e9;
+  const double gather_per_clk = (nbits == 16 ? 0.85 : 1.6) * (g.atmem ? 1.0 : 0.7);  // SS form: smaller L1 -> slower gathers
+  const double t_mma = 2.0 * g.n_tile;                                                 // 4 x (128 x N x 16) at 4096 MAC/clk
+  int best_tm = kGemmBlockM, best_ks = 1;
+  double best = 1e30;
+  const int max_ks = !allow_split ? 1 : (g.total_kblocks / 2 < 16 ? (g.total_kblocks / 2 < 1 ? 1 : g.total_kblocks / 2) : 16);
+  for (int tm = kGemmBlockM; tm >= 32; tm -= (tm > 64 ? 1 : 8)) {
+    const long long tiles = ((w->out_features + tm - 1) / tm) * (long long)g.n_tiles;
+    if (tiles > kGemmMaxTiles) continue;
+    const double t_gather = tm * 8.0 * K / gather_per_clk;
+    const double t_smem = (g.atmem ? 0.0 : (128.0 + tm) * 128.0 / 128.0) + 2.0 * g.n_tile;  // bytes / (128 B/clk)
+    const double t_kb = (t_gather > t_mma ? (t_gather > t_smem ? t_gather : t_smem) : (t_mma > t_smem ? t_mma : t_smem)) + 60.0;
     for (int c = 1; c <= max_ks; ++c) {
-      const double ctas = tiles * c;
+      const double ctas = (double)tiles * c;
       const double waves = (double)((long long)((ctas + di->sm_count - 1) / di->sm_count));
-      const double eff = ctas / (waves * di->sm_count);
-      const double fix = c > 1 ? ctas * g.n_tile * kGemmBlockM * 4.0 * 2.0 / 4e12 : 0.0;
-      // every wave pays the CTA's fixed costs again (launch ramp, TMEM alloc, pipeline fill, epilogue): ~5 us measured
-      const double t = t_gather / eff + fix + waves * 5e-6;
-      if (t < best * 0.97) {  // prefer fewer splits unless the gain is real
+      const double kb_cta = (double)((g.total_kblocks + c - 1) / c);
+      const double fix = c > 1 ? ctas * g.n_tile * kGemmBlockM * 4.0 * 2.0 / 4e12 * clk : 0.0;
+      const double t = waves * (kb_cta * t_kb + 5e-6 * clk) + fix;
+      if (t < best * (tm == kGemmBlockM && c == 1 ? 1.0 : 0.97)) {  // prefer full tiles / fewer splits unless the gain is real
         best = t;
-        ks = c;
+        best_tm = tm;
+        best_ks = c;
       }
     }
-    const int forced = tun().gemm_ksplit;
-    if (forced > 0) ks = forced;
-    if (ks > g.total_kblocks) ks = g.total_kblocks;
-    if (ks < 1) ks = 1;
   }
+  g.tile_m = best_tm;
+  int ks = best_ks;
+  if (tun().gemm_tile_m >= 8 && tun().gemm_tile_m <= kGemmBlockM) g.tile_m = tun().gemm_tile_m;
+  g.m_tiles = (int)((w->out_features + g.tile_m - 1) / g.tile_m);
+  if (allow_split && tun().gemm_ksplit > 0) ks = tun().gemm_ksplit;
+  if (ks > g.total_kblocks) ks = g.total_kblocks;
+  if (ks < 1) ks = 1;
   // fixed-size counter region (the partials of one plan must never overlap the counters of another plan that
   // reuses the same persistent workspace)
   g.counters_bytes = kWsCountersBytes;
@@ -502,7 +521,7 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
     const size_t row_bytes = (size_t)(w->in_features / 8) * K * CB;
     cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)w->out_features};
     cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)kCodeTileBytes, (cuuint32_t)kGemmBlockM};
+    cuuint32_t box[2] = {(cuuint32_t)kCodeTileBytes, (cuuint32_t)g.tile_m};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&tc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w->codes), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -523,18 +542,19 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   p.ksplit = g.ksplit;
   p.n_tile = g.n_tile;
   p.stages = g.stages;
+  p.tile_m = g.tile_m;
   p.cluster = g.cluster;
   p.debug = tun().gemm_debug;
   p.gather_mode = tun().gemm_gather_mode;
   p.codes = w->codes;
   p.row_bytes = (long long)(w->in_features / 8) * K * CB;
-  const size_t smem = gemm_smem_layout(g.stages, g.n_tile).total;
-  // producer mapping V2 (one 4-warp group per stage) measured: 1x16 496 vs 505 TFLOP/s (V1), 2x8 134 vs 394, 8x8 196 vs 119
-  // -> default only for schemes with many codebooks (profiles/r01/gemm_experiments.md)
-  const bool v2 = (tun().gemm_v2 < 0 ? (K >= 4 ? 1 : 0) : tun().gemm_v2) != 0 && g.stages <= 3 && !(p.debug & 1);
-  auto kernel = v2 ? gemm_dequant_kernel<T, K, CB, true> : gemm_dequant_kernel<T, K, CB, false>;
-  static SmemMarks marks[2];
-  if (int rc = ensure_smem(kernel, smem, marks[v2 ? 1 : 0], di)) return rc;
+  const size_t smem = gemm_smem_layout(g.stages, g.n_tile, g.atmem).total;
+  const bool v2 = g.v2 && g.stages <= 3;
+  const bool atmem = g.atmem && v2;
+  auto kernel = atmem ? gemm_dequant_kernel<T, K, CB, true, true>
+                      : (v2 ? gemm_dequant_kernel<T, K, CB, true, false> : gemm_dequant_kernel<T, K, CB, false, false>);
+  static SmemMarks marks[3];
+  if (int rc = ensure_smem(kernel, smem, marks[atmem ? 2 : (v2 ? 1 : 0)], di)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.m_tiles, g.ksplit, g.n_tiles);
   cfg.blockDim = dim3(v2 ? kGemmThreadsV2 : kGemmThreads);
@@ -564,6 +584,142 @@ static int gemm_typed(const aqlm_b200_weight_t* w, const void* input, void* outp
   if (K == 2) return launch_gemm<T, 2, 1>(w, input, output, batch, g, workspace, st);
   if (K == 4) return launch_gemm<T, 4, 1>(w, input, output, batch, g, workspace, st);
   return launch_gemm<T, 8, 1>(w, input, output, batch, g, workspace, st);
+}
+
+// ---- fused dequant + TRANSPOSED tcgen05 GEMM (backward w.r.t. the input): host side ---------------------
+struct GemmTPlan {
+  bool ok = false;
+  int m_tiles = 0, n_tiles = 0, n_tile = 0, ksplit = 1, stages = 0, total_kblocks = 0;
+  size_t counters_bytes = 0, partials_bytes = 0;
+};
+
+static GemmTPlan gemm_t_plan(const aqlm_b200_weight_t* w, int64_t batch, const DeviceInfo* di, bool allow_split) {
+  GemmTPlan g;
+  const int K = w->num_codebooks, nbits = w->nbits_per_codebook;
+  const int cb = nbits <= 8 ? 1 : 2;
+  if (w->in_group_size != 8 || (nbits != 8 && nbits != 16)) return g;
+  if (!(K == 1 || K == 2 || K == 4 || K == 8) || 16 * K * cb > 256) return g;
+  if (w->out_features % 8 != 0) return g;  // TMA row stride of grad_out
+  if ((reinterpret_cast<uintptr_t>(w->codes) & 15) != 0) return g;
+  if (((size_t)(w->in_features / 8) * K * cb) % 16 != 0) return g;
+  if (tun().disable_tcgen05) return g;
+  g.total_kblocks = (int)((w->out_features + kGemmBlockK - 1) / kGemmBlockK);
+  g.m_tiles = (int)((w->in_features + kGemmBlockM - 1) / kGemmBlockM);
+  if (batch <= 256) {
+    g.n_tile = (int)((batch + 15) / 16 * 16);
+    g.n_tiles = 1;
+  } else {
+    g.n_tile = 256;
+    g.n_tiles = (int)((batch + 255) / 256);
+  }
+  const int ctile_row_bytes = 16 * K * cb;
+  const size_t budget = (size_t)di->max_smem_optin;
+  int S = 3;
+  while (S > 2 && gemm_t_smem_layout(S, g.n_tile, ctile_row_bytes).total > budget) --S;
+  if (gemm_t_smem_layout(S, g.n_tile, ctile_row_bytes).total > budget) return g;
+  if (tun().gemm_stages >= 2 && tun().gemm_stages <= S) S = tun().gemm_stages;
+  g.stages = S;
+  if ((size_t)g.m_tiles * g.n_tiles > (size_t)kGemmMaxTiles) return g;
+  int ks = 1;
+  if (allow_split) {
+    // same cost model as the forward plan: a k-block costs max(gathers, tensor pipe, smem traffic), every wave pays a
+    // fixed ~5 us, split-K partials go through L2 once each way
+    const double clk = 1.9e9;
+    const double t_gather = 1024.0 * K / ((nbits == 16 ? 0.85 : 1.6) * 0.7);
+    const double t_smem = 256.0 + 2.0 * g.n_tile, t_mma = 2.0 * g.n_tile;
+    const double t_kb = (t_gather > t_smem ? (t_gather > t_mma ? t_gather : t_mma) : (t_smem > t_mma ? t_smem : t_mma)) + 60.0;
+    const double tiles = (double)g.m_tiles * g.n_tiles;
+    double best = 1e30;
+    const int max_ks = g.total_kblocks / 2 < 16 ? (g.total_kblocks / 2 < 1 ? 1 : g.total_kblocks / 2) : 16;
+    for (int c = 1; c <= max_ks; ++c) {
+      const double ctas = tiles * c;
+      const double waves = (double)((long long)((ctas + di->sm_count - 1) / di->sm_count));
+      const double kb_cta = (double)((g.total_kblocks + c - 1) / c);
+      const double fix = c > 1 ? ctas * g.n_tile * kGemmBlockM * 4.0 * 2.0 / 4e12 * clk : 0.0;
+      const double t = waves * (kb_cta * t_kb + 5e-6 * clk) + fix;
+      if (t < best * 0.97) {
+        best = t;
+        ks = c;
+      }
+    }
+    if (tun().gemm_ksplit > 0) ks = tun().gemm_ksplit;
+    if (ks > g.total_kblocks) ks = g.total_kblocks;
+    if (ks < 1) ks = 1;
+  }
+  g.ksplit = ks;
+  g.counters_bytes = kWsCountersBytes;
+  g.partials_bytes = ks > 1 ? (size_t)g.m_tiles * g.n_tiles * ks * g.n_tile * kGemmBlockM * 4 : 0;
+  g.ok = true;
+  return g;
+}
+
+template <typename T, int K, int CB>
+static int launch_gemm_t(const aqlm_b200_weight_t* w, const void* grad_output, void* grad_input, int64_t batch,
+                         const GemmTPlan& g, void* workspace, cudaStream_t st) {
+  const DeviceInfo* di = device_info();
+  if (!di) return AQLM_B200_ERR_CUDA;
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc) return fail(AQLM_B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  constexpr int GBT = 16 * K * CB;
+  CUtensorMap tg, tc;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)w->out_features, (cuuint64_t)batch};
+    cuuint64_t strides[1] = {(cuuint64_t)w->out_features * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)g.n_tile};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tg, DT<T>::is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void*>(grad_output), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AQLM_B200_ERR_CUDA, "cuTensorMapEncodeTiled(grad_output) failed: %d", (int)r);
+  }
+  {
+    const size_t row_bytes = (size_t)(w->in_features / 8) * K * CB;
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)w->out_features};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)GBT, (cuuint32_t)kGemmTCtileRows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w->codes), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AQLM_B200_ERR_CUDA, "cuTensorMapEncodeTiled(codes, transposed) failed: %d", (int)r);
+  }
+  GemmTParams p;
+  p.codebooks = w->codebooks;
+  p.scales = w->scales;
+  p.y = grad_input;
+  p.ws_counters = g.ksplit > 1 ? reinterpret_cast<unsigned int*>(workspace) : nullptr;
+  p.ws_partials = g.ksplit > 1 ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + g.counters_bytes) : nullptr;
+  p.in_features = (int)w->in_features;
+  p.out_features = (int)w->out_features;
+  p.batch = (int)batch;
+  p.nbits = w->nbits_per_codebook;
+  p.total_kblocks = g.total_kblocks;
+  p.ksplit = g.ksplit;
+  p.n_tile = g.n_tile;
+  p.stages = g.stages;
+  p.gather_mode = tun().gemm_gather_mode;
+  const size_t smem = gemm_t_smem_layout(g.stages, g.n_tile, GBT).total;
+  auto kernel = gemm_dequant_t_kernel<T, K, CB>;
+  static SmemMarks marks;
+  if (int rc = ensure_smem(kernel, smem, marks, di)) return rc;
+  kernel<<<dim3(g.m_tiles, g.ksplit, g.n_tiles), kGemmTThreads, smem, st>>>(tg, tc, p);
+  count_launch();
+  AQLM_CUDA_CHECK(cudaGetLastError());
+  return AQLM_B200_OK;
+}
+
+template <typename T>
+static int gemm_t_typed(const aqlm_b200_weight_t* w, const void* grad_output, void* grad_input, int64_t batch,
+                        const GemmTPlan& g, void* workspace, cudaStream_t st) {
+  const int K = w->num_codebooks, cb = w->nbits_per_codebook <= 8 ? 1 : 2;
+  if (cb == 2 && K == 1) return launch_gemm_t<T, 1, 2>(w, grad_output, grad_input, batch, g, workspace, st);
+  if (cb == 2 && K == 2) return launch_gemm_t<T, 2, 2>(w, grad_output, grad_input, batch, g, workspace, st);
+  if (cb == 2 && K == 4) return launch_gemm_t<T, 4, 2>(w, grad_output, grad_input, batch, g, workspace, st);
+  if (cb == 2 && K == 8) return launch_gemm_t<T, 8, 2>(w, grad_output, grad_input, batch, g, workspace, st);
+  if (K == 1) return launch_gemm_t<T, 1, 1>(w, grad_output, grad_input, batch, g, workspace, st);
+  if (K == 2) return launch_gemm_t<T, 2, 1>(w, grad_output, grad_input, batch, g, workspace, st);
+  if (K == 4) return launch_gemm_t<T, 4, 1>(w, grad_output, grad_input, batch, g, workspace, st);
+  return launch_gemm_t<T, 8, 1>(w, grad_output, grad_input, batch, g, workspace, st);
 }
 
 static aqlm_b200_weight_t make_weight(const void* codes, const void* codebooks, const void* scales, const void* bias,
@@ -736,10 +892,35 @@ int aqlm_b200_dequant(const aqlm_b200_weight_t* w, void* weight_out, int apply_s
   return dequant_typed<__nv_bfloat16>(w, weight_out, apply_scales, st);
 }
 
+size_t aqlm_b200_matmat_dequant_transposed_workspace_bytes(const aqlm_b200_weight_t* w, int64_t batch) {
+  if (validate(w, true) != AQLM_B200_OK || batch <= 0) return 0;
+  const DeviceInfo* di = device_info();
+  if (!di) return 0;
+  const GemmTPlan g = gemm_t_plan(w, batch, di, true);
+  if (!g.ok || g.ksplit <= 1) return 0;
+  return g.counters_bytes + g.partials_bytes;
+}
+
 int aqlm_b200_matmat_dequant_transposed(const aqlm_b200_weight_t* w, const void* grad_output, void* grad_input,
-                                        int64_t batch, void* workspace, void* stream) {
-  (void)w; (void)grad_output; (void)grad_input; (void)batch; (void)workspace; (void)stream;
-  return fail(AQLM_B200_ERR_UNSUPPORTED, "matmat_dequant_transposed (backward) is not implemented yet (SURVEY §8f.3)");
+                                        int64_t batch, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate(w, true);
+  if (rc) return rc;
+  if (batch < 0) return fail(AQLM_B200_ERR_SHAPE, "negative batch");
+  if (batch == 0) return AQLM_B200_OK;
+  if (!grad_output || !grad_input) return fail(AQLM_B200_ERR_SHAPE, "grad_output/grad_input pointer is NULL");
+  if ((reinterpret_cast<uintptr_t>(grad_output) & 15) != 0)
+    return fail(AQLM_B200_ERR_SHAPE, "grad_output must be 16-byte aligned");
+  const DeviceInfo* di = device_info();
+  if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
+  GemmTPlan g = gemm_t_plan(w, batch, di, workspace != nullptr);
+  if (g.ok && g.ksplit > 1 && workspace_bytes < g.counters_bytes + g.partials_bytes) g = gemm_t_plan(w, batch, di, false);
+  if (!g.ok)
+    return fail(AQLM_B200_ERR_UNSUPPORTED,
+                "matmat_dequant_transposed: the fused kernel covers in_group_size 8, 8/16-bit codes, 1/2/4/8 codebooks, "
+                "16-byte aligned code rows and out_features %% 8 == 0");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (w->dtype == AQLM_B200_F16) return gemm_t_typed<__half>(w, grad_output, grad_input, batch, g, workspace, st);
+  return gemm_t_typed<__nv_bfloat16>(w, grad_output, grad_input, batch, g, workspace, st);
 }
 
 int aqlm_b200_scale_bias(const float* partial, const void* scales, const void* bias, void* output, int64_t batch,

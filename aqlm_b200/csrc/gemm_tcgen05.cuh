@@ -46,6 +46,7 @@ struct GemmParams {
   int n_tile;           // N of the MMA (multiple of 16, <= 256)
   int stages;
   int cluster;          // CTAs per cluster along M that share (multicast) the X tiles
+  int tile_m;           // output rows per CTA tile (<= 128): ragged tile heights balance the grid (e.g. 97 rows -> 148 tiles of 14336)
   int gather_mode;      // 0: ld.global.nc (L1 allocate), 1: ld.global.cg, 3: nc.L1::no_allocate
   int debug;            // bit0: read codes from global instead of the TMA code tile; bit1: no producer run-ahead
   const void* codes;    // (debug bit0)
@@ -109,6 +110,25 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
       "r"(accumulate) : "memory");
 }
+// same with the A operand in tensor memory (lane = row, 32-bit column c holds K elements 2c, 2c+1)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc),
+      "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 columns: thread t of the warp writes r[0..31] to TMEM lane (32*(warp%4) + t), columns [col, col+32)
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -129,10 +149,10 @@ struct GemmSmem {
   uint32_t a, b, codes, full, empty, cfull, cempty, tfull, tmem_slot, flag;
   size_t total;
 };
-__host__ __device__ inline GemmSmem gemm_smem_layout(int stages, int n_tile) {
+__host__ __device__ inline GemmSmem gemm_smem_layout(int stages, int n_tile, bool a_in_tmem = false) {
   GemmSmem L;
   size_t off = 0;
-  L.a = (uint32_t)off; off += (size_t)stages * kGemmBlockM * 128;
+  L.a = (uint32_t)off; off += a_in_tmem ? 0 : (size_t)stages * kGemmBlockM * 128;
   L.b = (uint32_t)off; off += (size_t)stages * n_tile * 128;
   off = (off + 1023) & ~(size_t)1023;
   L.codes = (uint32_t)off; off += (size_t)kCodeTileStages * kGemmBlockM * kCodeTileBytes;
@@ -149,9 +169,15 @@ __host__ __device__ inline GemmSmem gemm_smem_layout(int stages, int n_tile) {
 
 // K = codebooks per group, CODE_BYTES = 1|2 ; in_group_size == 8.
 // bytes of codes per row per 64-wide k-block: GB = 8 groups * K * CODE_BYTES
-template <typename T, int K, int CODE_BYTES, bool V2>
+// ATMEM (needs the V2 producer mapping, thread <-> row): the dequantized A tile is written to TENSOR MEMORY with tcgen05.st
+// and the MMA takes A from TMEM.  Shared memory then carries only the X stages (and the code tiles): per k-block the
+// shared-memory traffic drops from 96 KB (A write + A read + X write + X read at N=256) to 64 KB -- at 128 B/clk that was
+// 768 clk against 512 clk of MMA, i.e. the SS form was shared-memory bound before any gather -- and the L1 the gathers
+// run against grows by the 48 KB the A stages took.
+template <typename T, int K, int CODE_BYTES, bool V2, bool ATMEM = false>
 __global__ void __launch_bounds__(V2 ? kGemmThreadsV2 : kGemmThreads, 1)
 gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_codes, const GemmParams p) {
+  static_assert(!ATMEM || V2, "A-in-TMEM needs the thread <-> row producer mapping");
   constexpr int NTHREADS = V2 ? kGemmThreadsV2 : kGemmThreads;
   constexpr int GB = 8 * K * CODE_BYTES;             // code bytes per row per k-block
   constexpr int KB_PER_CTILE = kCodeTileBytes / GB;  // k-blocks covered by one code tile
@@ -159,8 +185,9 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* gbase = smem_dyn + (base - smem_u32(smem_dyn));
-  const GemmSmem L = gemm_smem_layout(p.stages, p.n_tile);
+  const GemmSmem L = gemm_smem_layout(p.stages, p.n_tile, ATMEM);
   const int S = p.stages;
+  const int TM = p.tile_m;
   const int N = p.n_tile;
   const int C = p.cluster;
   const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
@@ -168,7 +195,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, split = blockIdx.y, n_blk = blockIdx.z;
-  const int m0 = m_tile * kGemmBlockM, n0 = n_blk * N;
+  const int m0 = m_tile * TM, n0 = n_blk * N;
   // k-block range of this split (balanced, contiguous)
   const int kb0 = (int)(((long long)p.total_kblocks * split) / p.ksplit);
   const int kb1 = (int)(((long long)p.total_kblocks * (split + 1)) / p.ksplit);
@@ -196,8 +223,10 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     mbar_init(tfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // accumulator: columns [0, N); with ATMEM the A stages follow at a 32-column aligned offset, 32 columns per stage
+  const uint32_t a_col0 = (uint32_t)((N + 31) & ~31);
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < N) tmem_cols <<= 1;
+  while (tmem_cols < (ATMEM ? a_col0 + 32u * (uint32_t)S : (uint32_t)N)) tmem_cols <<= 1;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L.tmem_slot), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -216,7 +245,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int cs = (ct - ct0) % kCodeTileStages;
         const int it = (ct - ct0) / kCodeTileStages;
         if (it > 0) mbar_wait(cempty_bar(cs), (it - 1) & 1);  // every producer warp released the previous tenant
-        mbar_expect_tx(cfull_bar(cs), kGemmBlockM * kCodeTileBytes);
+        mbar_expect_tx(cfull_bar(cs), (uint32_t)TM * kCodeTileBytes);  // the TMA box is tile_m rows tall
         tma_load_2d(base + L.codes + cs * kGemmBlockM * kCodeTileBytes, &tmap_codes, ct * kCodeTileBytes, m0, cfull_bar(cs));
       };
       load_ctile(ct_loaded++);
@@ -251,7 +280,10 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const uint32_t b_addr = base + L.b + s * N * 128;
 #pragma unroll
         for (int k = 0; k < kGemmBlockK / 16; ++k) {
-          umma_f16(tmem_base, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc, (i | k) ? 1u : 0u);
+          if constexpr (ATMEM)
+            umma_f16_ts(tmem_base, tmem_base + a_col0 + (uint32_t)(s * 32 + k * 8), umma_desc_k128(b_addr + k * 32), idesc, (i | k) ? 1u : 0u);
+          else
+            umma_f16(tmem_base, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc, (i | k) ? 1u : 0u);
         }
         // frees this smem stage (in every CTA of the cluster) when the MMAs above have read it
         if (C == 1) umma_commit(empty_bar(s));
@@ -265,6 +297,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int g = pw >> 2;
         if (g < S) {
           const int row = (pw & 3) * 32 + lane;
+          const bool active = row < TM;  // rows past the (ragged) tile height: no gathers, nothing to write
           const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
           constexpr int CWN = GB / 4 > 0 ? GB / 4 : 1;  // 32-bit words of codes per row per k-block
           constexpr bool INREG = (K <= 2);               // gather in issue() and hold the vectors in registers
@@ -287,7 +320,10 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             const int cs = (ct - ct0) % kCodeTileStages, cit = (ct - ct0) / kCodeTileStages;
             mbar_wait(cfull_bar(cs), cit & 1);
             const uint8_t* crow = gbase + L.codes + cs * kGemmBlockM * kCodeTileBytes + row * 128;
-            if constexpr (GB >= 16) {
+            if (!active) {
+#pragma unroll
+              for (int q = 0; q < CWN; ++q) cw[q] = 0u;
+            } else if constexpr (GB >= 16) {
 #pragma unroll
               for (int q = 0; q < GB / 16; ++q) {
                 const int chunk = ((st_in * GB) / 16 + q) ^ (row & 7);
@@ -307,20 +343,29 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           };
           auto gather_all = [&](const uint32_t (&cw)[CWN], uint4 (&wv)[8][INREG ? K : 1]) {
             if constexpr (INREG) {
+              if (active) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
+                for (int e = 0; e < 8; ++e)
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                  const uint4* gp = gcb + (((size_t)k << p.nbits) + code_at(cw, e * K + k));
-                  if (p.gather_mode == 1) wv[e][k] = ld_gather_v4<1>(gp);
-                  else wv[e][k] = ld_gather_v4<0>(gp);
-                }
+                  for (int k = 0; k < K; ++k) {
+                    const uint4* gp = gcb + (((size_t)k << p.nbits) + code_at(cw, e * K + k));
+                    if (p.gather_mode == 1) wv[e][k] = ld_gather_v4<1>(gp);
+                    else wv[e][k] = ld_gather_v4<0>(gp);
+                  }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+#pragma unroll
+                  for (int k = 0; k < K; ++k) wv[e][k] = make_uint4(0u, 0u, 0u, 0u);
+              }
             }
           };
           auto commit = [&](int i, const uint32_t (&cw)[CWN], uint4 (&wv)[8][INREG ? K : 1]) {
             const int s = i % S, it = i / S;
             if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
             uint8_t* arow = gbase + L.a + s * kGemmBlockM * 128 + row * 128;
+            uint32_t areg[32];  // ATMEM: the row's 64 halves in K order (= the TMEM column order)
+            if constexpr (ATMEM) tc_fence_after();  // the stage's previous reader (MMA) is ordered before these writes
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               uint4 v;
@@ -332,20 +377,34 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                   unpack8<T>(wv[e][0], f);
 #pragma unroll
                   for (int k = 1; k < K; ++k) accum8<T>(wv[e][k], f);
-                } else {  // many codebooks: gather group by group (the 4-32 KiB codebooks are L1-resident)
+                } else if (active) {  // many codebooks: gather group by group (the 4-32 KiB codebooks are L1-resident)
                   uint4 t[K];
 #pragma unroll
                   for (int k = 0; k < K; ++k) t[k] = ld_gather_v4<0>(gcb + (((size_t)k << p.nbits) + code_at(cw, e * K + k)));
                   unpack8<T>(t[0], f);
 #pragma unroll
                   for (int k = 1; k < K; ++k) accum8<T>(t[k], f);
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) f[q] = 0.f;
                 }
                 v.x = DT<T>::pack2(f[0], f[1]); v.y = DT<T>::pack2(f[2], f[3]);
                 v.z = DT<T>::pack2(f[4], f[5]); v.w = DT<T>::pack2(f[6], f[7]);
               }
-              *reinterpret_cast<uint4*>(arow + ((e ^ (row & 7)) << 4)) = v;
+              if constexpr (ATMEM) {
+                areg[4 * e + 0] = v.x; areg[4 * e + 1] = v.y; areg[4 * e + 2] = v.z; areg[4 * e + 3] = v.w;
+              } else {
+                if (active) *reinterpret_cast<uint4*>(arow + ((e ^ (row & 7)) << 4)) = v;
+              }
             }
-            fence_proxy_async();
+            if constexpr (ATMEM) {
+              // warp-collective store of 32 rows x 32 columns into this warp's TMEM quadrant, then make it visible to the
+              // MMA thread: wait::st -> fence::before_thread_sync -> mbarrier arrive
+              tmem_st_32x32b_x32(tmem_base + ((uint32_t)((pw & 3) * 32) << 16) + a_col0 + (uint32_t)(s * 32), areg);
+              tc_fence_before();
+            } else {
+              fence_proxy_async();
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(s));
           };
@@ -378,6 +437,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       // Software-pipelined: the gathers of k-block i+1 are in flight while k-block i is written to smem.
       const int pt = threadIdx.x - 128;
       const int row = pt >> 2, gq = pt & 3;
+      const bool active = row < TM;  // rows past the (ragged) tile height: no gathers, nothing to write
       const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
       constexpr int CB2 = 2 * K * CODE_BYTES;  // code bytes of this thread's 2 groups
       constexpr int CW = (CB2 + 3) / 4;        // 32-bit words holding them
@@ -390,7 +450,10 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int cs = (ct - ct0) % kCodeTileStages, cit = (ct - ct0) / kCodeTileStages;
         mbar_wait(cfull_bar(cs), cit & 1);
         uint32_t cw[CW];
-        if (p.debug & 1) {
+        if (!active) {
+#pragma unroll
+          for (int q = 0; q < CW; ++q) cw[q] = 0u;
+        } else if (p.debug & 1) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(p.codes) + (size_t)(m0 + row) * p.row_bytes + (size_t)kb * GB + gq * CB2;
 #pragma unroll
           for (int q = 0; q < CW; ++q) {
@@ -426,7 +489,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             if constexpr (CODE_BYTES == 2) code = (cw[idx >> 1] >> ((idx & 1) * 16)) & 0xffffu;
             else code = (cw[idx >> 2] >> ((idx & 3) * 8)) & 0xffu;
             const uint4* gp = gcb + (((size_t)k << p.nbits) + code);
-            if (p.debug & 8) wv[e][k] = make_uint4(code, code, code, code);  // experiment: no gathers
+            if (!active || (p.debug & 8)) wv[e][k] = make_uint4(code, code, code, code);  // inactive row / experiment: no gathers
             else if (p.gather_mode == 1) wv[e][k] = ld_gather_v4<1>(gp);       // ld.global.cg (L2 only)
             else if (p.gather_mode == 3) wv[e][k] = ld_gather_v4<3>(gp);       // nc + L1::no_allocate
             else wv[e][k] = ld_gather_v4<0>(gp);
@@ -457,7 +520,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             v.z = DT<T>::pack2(f[4], f[5]); v.w = DT<T>::pack2(f[6], f[7]);
           }
           const int j = gq * 2 + e;  // 16-byte chunk (= group) index inside the 128-byte K row
-          *reinterpret_cast<uint4*>(arow + ((j ^ (row & 7)) << 4)) = v;
+          if (active) *reinterpret_cast<uint4*>(arow + ((j ^ (row & 7)) << 4)) = v;
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -489,7 +552,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     __syncwarp();  // lanes 1-31 of the TMA / MMA warps wait here for their lane 0 (tcgen05.ld is warp-collective)
     const int row_in_tile = warp * 32 + lane;
     const int row = m0 + row_in_tile;
-    const bool row_ok = row < p.out_features;
+    const bool row_ok = row_in_tile < TM && row < p.out_features;
     float sc = 1.f, bi = 0.f;
     if (row_ok && p.ksplit == 1) {
       sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
@@ -541,7 +604,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const int cphase = threadIdx.x >> 7;
       constexpr int kPhases = NTHREADS / kGemmBlockM;
       const int row = m0 + rrow;
-      if (row < p.out_features) {
+      if (rrow < TM && row < p.out_features) {
         const float sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
         const float bi = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
         const int ncols = min(N, p.batch - n0);

@@ -246,18 +246,43 @@ def dequant(codes, codebooks, scales=None) -> torch.Tensor:
 
 
 def matmat_dequant_transposed(input, codes, codebooks, scales, bias=None) -> torch.Tensor:
-    """Backward w.r.t. the input: (grad_out * scales) @ W_unscaled (reference cuda_kernel.cpp:303-354).
+    """Backward w.r.t. the input: grad_in = (grad_out * scales) @ W_unscaled (reference cuda_kernel.cpp:303-354).
 
-    Dequant is our kernel; the dense contraction is a LIBRARY GEMM (torch.matmul -> cuBLAS), exactly as in the
-    reference (F::linear, cuda_kernel.cpp:353).  The reference's 2x8/1x8 variants forget to use the scaled
-    input (cuda_kernel.cpp:497,518,662,683); that defect is not reproduced.
+    ONE fused kernel (csrc/gemm_tcgen05_t.cuh): W^T tiles are dequantized on chip into an MN-major tcgen05 operand, the
+    per-row scale is folded into the tile, grad_out tiles arrive by TMA; W is never materialised and no library GEMM is
+    called.  The reference's 2x8/1x8 variants forget the scaled input (cuda_kernel.cpp:497,518,662,683); not reproduced.
+    `bias` is the forward bias [out]; it has no place in grad_input (the reference passes it to F::linear,
+    cuda_kernel.cpp:348-353, which only type-checks when in == out) and is ignored.
+    Layouts the fused kernel does not cover (in_group_size 16, odd codebook counts) fall back to our dequant kernel +
+    a dense matmul, as the reference does for every scheme.
     """
-    _require_cuda(input, codes, codebooks, scales, bias)
-    weight = dequant(codes, codebooks, None)  # unscaled [out, in]
-    scaled = input.reshape(-1, input.shape[-1]) * scales.reshape(1, -1)
-    out = scaled @ weight  # `bias` is the forward bias [out]; it has no place in grad_input (the reference passes
-    # it to F::linear, cuda_kernel.cpp:348-353, which only type-checks when in == out) -- ignored here.
-    return out.reshape(input.shape[:-1] + (weight.shape[1],))
+    device = _require_cuda(input, codes, codebooks, scales)
+    _dtype_code(input)
+    if input.dtype != codebooks.dtype:
+        raise ValueError(f"grad_output dtype {input.dtype} != codebooks dtype {codebooks.dtype}")
+    w = make_weight(codes, codebooks, scales.reshape(-1), None)
+    if input.shape[-1] != w.out_features:
+        raise ValueError(f"grad_output has {input.shape[-1]} features, weight has {w.out_features} output rows")
+    flat = input.reshape(-1, input.shape[-1])
+    if not flat.is_contiguous():
+        flat = flat.contiguous()
+    batch = flat.shape[0]
+    out = torch.empty((batch, w.in_features), dtype=input.dtype, device=device)
+    if batch == 0:
+        return out.reshape(input.shape[:-1] + (w.in_features,))
+    with _on_device(device):
+        L = _cabi.lib()
+        need = L.aqlm_b200_matmat_dequant_transposed_workspace_bytes(ctypes.byref(w), batch)
+        ws = _workspace(device, need) if need else None
+        rc = L.aqlm_b200_matmat_dequant_transposed(ctypes.byref(w), flat.data_ptr(), out.data_ptr(), batch,
+                                                   ws.data_ptr() if ws is not None else None,
+                                                   ws.numel() if ws is not None else 0, _stream_ptr(device))
+    if rc == _cabi.ERR_UNSUPPORTED:
+        weight = dequant(codes, codebooks, None)  # unscaled [out, in]
+        out = (flat * scales.reshape(1, -1)) @ weight
+    else:
+        _cabi.check(rc)
+    return out.reshape(input.shape[:-1] + (w.in_features,))
 
 
 # ---- torch.library registration (reference cuda_kernel.py:13-132) ---------------------------------------

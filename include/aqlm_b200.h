@@ -109,12 +109,15 @@ int aqlm_b200_matmat_dequant_ws(const aqlm_b200_weight_t* w, const void* input, 
  * code{1x16,2x8,1x8}_dequant (cuda_kernel.cpp:184-227, 423-448, 588-613). */
 int aqlm_b200_dequant(const aqlm_b200_weight_t* w, void* weight_out, int apply_scales, void* stream);
 
-/* grad_input[batch, in] = (grad_output * scales) @ W_unscaled.  Replaces
- * code*_matmat_dequant_transposed (cuda_kernel.cpp:303-354, 486-519, 651-684), with the 2x8/1x8
- * unscaled-input defect (cuda_kernel.cpp:497,518,662,683) NOT reproduced.  `workspace` must hold
- * out_features*in_features elements of the weight dtype. */
+/* Backward w.r.t. the input, fused: grad_input[batch, in] = (grad_output[batch, out] * scales) @ W_unscaled, with W
+ * dequantized on chip (MN-major A tile, tcgen05 MMA, scale folded into the tile) -- W never goes to HBM and no library
+ * GEMM is involved.  Replaces code*_matmat_dequant_transposed (cuda_kernel.cpp:303-354, 486-519, 651-684: Dequant
+ * kernel -> full W in HBM -> cuBLAS), with the 2x8/1x8 unscaled-input defect (cuda_kernel.cpp:497,518,662,683) NOT
+ * reproduced.  The optional workspace (same zero-init contract as aqlm_b200_matmat_dequant_ws) enables split-K over the
+ * out rows.  Returns AQLM_B200_ERR_UNSUPPORTED for layouts the fused kernel does not cover (in_group_size 16, ...). */
+size_t aqlm_b200_matmat_dequant_transposed_workspace_bytes(const aqlm_b200_weight_t* w, int64_t batch);
 int aqlm_b200_matmat_dequant_transposed(const aqlm_b200_weight_t* w, const void* grad_output, void* grad_input,
-                                        int64_t batch, void* workspace, void* stream);
+                                        int64_t batch, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Epilogue of the sharded path: output[b,o] = (T)(partial[b,o] * scales[o] + bias[o]) after the
  * all-reduce of the fp32 partials (new work; the reference has no multi-GPU hot path). */

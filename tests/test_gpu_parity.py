@@ -366,6 +366,77 @@ def test_gemm_1x8_row_stride_not_tma_compatible_falls_back():
     assert O.relative_error(y, oracle_output(case)) < TOL_FP16_TIGHT
 
 
+# ---- fused dequant-transpose GEMM (backward w.r.t. the input) ------------------------------------
+def _transposed_ref(t, go):
+    """(grad_out * scales) @ W_unscaled with the C oracle's dequantized weights, fp32 (reference cuda_kernel.cpp:303-354)."""
+    from oracle import c_oracle
+
+    f32 = lambda a: a.float().cpu().numpy()  # noqa: E731
+    W = c_oracle.dequantize_weight(t["codes"].cpu().numpy(), f32(t["codebooks"]), f32(t["scales"]))  # scaled rows
+    return f32(go) @ W
+
+
+@pytest.mark.parametrize("K,nbits", [(1, 16), (2, 8), (1, 8), (8, 8), (4, 8)])
+@pytest.mark.parametrize("batch", [1, 7, 64, 256, 300])
+def test_transposed_gemm_vs_oracle_small(K, nbits, batch):
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    fin, fout = (512, 200) if batch != 64 else (1152, 456)  # ragged in both dims: in % 128 != 0, out % 64 != 0
+    t = gpu_case(fin, fout, K, nbits, 1, seed=8300 + K + nbits + batch)
+    go = torch.randn((batch, fout), dtype=torch.float16, device=DEV)
+    before = aqlm_launches()
+    gx = cuda_kernel.matmat_dequant_transposed(go, t["codes"], t["codebooks"], t["scales"], None)
+    assert aqlm_launches() == before + 1, "the backward must be ONE fused kernel (no dequant + library GEMM)"
+    assert gx.shape == (batch, fin)
+    assert O.relative_error(gx.float().cpu().numpy(), _transposed_ref(t, go)) < TOL_NORTH_STAR
+
+
+@pytest.mark.parametrize("K,nbits,shape,dtype", [(1, 16, (4096, 14336), torch.float16), (1, 16, (14336, 4096), torch.float16),
+                                                 (2, 8, (4096, 11008), torch.float16), (1, 16, (4096, 4096), torch.bfloat16)])
+def test_transposed_gemm_full_size(K, nbits, shape, dtype):
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    fin, fout = shape
+    t = gpu_case(fin, fout, K, nbits, 1, dtype=dtype, seed=8400 + fin)
+    go = torch.randn((256, fout), dtype=dtype, device=DEV)
+    gx = cuda_kernel.matmat_dequant_transposed(go, t["codes"], t["codebooks"], t["scales"], None)
+    rel = O.relative_error(gx.float().cpu().numpy(), _transposed_ref(t, go))
+    assert rel < (TOL_NORTH_STAR if dtype == torch.float16 else TOL_BF16), rel
+    gx2 = cuda_kernel.matmat_dequant_transposed(go, t["codes"], t["codebooks"], t["scales"], None)
+    assert torch.equal(gx, gx2)  # deterministic split-K
+
+
+def test_module_backward_uses_the_fused_kernel():
+    """autograd through QuantizedLinear at a training-size batch: grad w.r.t. the input comes from the fused kernel."""
+    case = O.make_case(8500, 1024, 384, 1, 16, 8, 32, False)
+    layer, t = make_module(case, DEV)
+    x = t["x"].clone().requires_grad_(True)
+    y = layer(x)
+    go = torch.randn_like(y)
+    before = aqlm_launches()
+    (gx,) = torch.autograd.grad(y, x, go)
+    assert aqlm_launches() == before + 1
+    W = O.dequantize_weight(O.unpack_int_data(case["codes"], 16), case["codebooks"], case["scales"])
+    assert O.relative_error(gx.float().cpu().numpy(), go.float().cpu().numpy() @ W) < TOL_NORTH_STAR
+
+
+def test_misaligned_input_through_the_c_abi():
+    """x only element-aligned (2 bytes off a 16-byte boundary): the C-ABI must take the slow path, not fault."""
+    from aqlm_b200 import _cabi
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    case = O.make_case(8600, 512, 64, 1, 16, 8, 1, True)
+    t = to_torch(case, DEV)
+    buf = torch.zeros(512 + 8, dtype=torch.float16, device=DEV)
+    buf[1:513] = t["x"][0]
+    w = cuda_kernel.make_weight(t["codes"], t["codebooks"], t["scales"].reshape(-1), t["bias"])
+    y = torch.empty((1, 64), dtype=torch.float16, device=DEV)
+    _cabi.check(_cabi.lib().aqlm_b200_matmat(ctypes.byref(w), buf.data_ptr() + 2, y.data_ptr(), 1,
+                                             torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert O.relative_error(y.float().cpu().numpy(), oracle_output(case)) < TOL_FP16_TIGHT
+
+
 # ---- full-size matvec parity against the C oracle (every output row) ------------------------------------------------
 LLAMA3_8B = [(4096, 4096), (4096, 1024), (4096, 14336), (14336, 4096)]
 LLAMA3_70B = [(8192, 8192), (8192, 1024), (8192, 28672), (28672, 8192)]

@@ -3,6 +3,10 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt
+# GEMM experiments first (short): A-in-TMEM / ragged tile heights vs the round-1 configuration
+timeout 600 python tools/probe_gemm.py --shapes 4096x14336,4096x4096 --batches 256 --settings "GEMM_ATMEM=0,GEMM_TILE_M=128;GEMM_ATMEM=0;GEMM_ATMEM=1,GEMM_TILE_M=128;GEMM_ATMEM=1;GEMM_ATMEM=1,GEMM_TILE_M=97,GEMM_STAGES=2;GEMM_ATMEM=1,GEMM_GATHER_MODE=0" > gpurun_out/probe_gemm_a.jsonl 2>&1
+cat gpurun_out/probe_gemm_a.jsonl
+export AQLM_B200_GEMM_ATMEM=0
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 timeout 1200 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
