@@ -101,6 +101,7 @@ def lib():
                 L.aqlm_b200_comm_partials.restype = vp
                 L.aqlm_b200_comm_destroy.argtypes = [vp]
                 L.aqlm_b200_allreduce_scale_bias.argtypes = [vp, vp, vp, vp, vp, i64, i64, i32, vp]
+                L.aqlm_b200_matmat_allreduce.argtypes = [vp, wp, ctypes.POINTER(i64), ctypes.c_int, vp, vp, i64, vp]
                 flat_mm_g = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp]
                 flat_mm = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, vp]
                 L.aqlm_b200_code1x16_matmat.argtypes = flat_mm_g

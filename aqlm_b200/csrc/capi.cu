@@ -178,7 +178,38 @@ static int launch_1x16_t(const GemvParams& p, const DeviceInfo* di, cudaStream_t
   attr[0].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
+  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p, GemvPeer{}));
+  count_launch();
+  return AQLM_B200_OK;
+}
+
+// Fused GEMV + peer-memory exchange (gemv_1x16_kernel<..., PEER = true>): contiguous row blocks, one CTA per SM.
+template <typename T, int BT>
+static int launch_1x16_peer(GemvParams p, const GemvPeer& pc, const DeviceInfo* di, cudaStream_t st) {
+  const int grid = di->sm_count;
+  if (grid > kPeerFlagStride) return fail(AQLM_B200_ERR_UNSUPPORTED, "fused exchange: more SMs than flag slots");
+  int rb = (p.out_features + grid - 1) / grid;
+  rb = (rb + 3) & ~3;
+  p.row_block = rb;
+  const int chunks = p.in_groups / 8;
+  const int slices = (chunks + kSliceChunks - 1) / kSliceChunks;
+  const size_t smem = (size_t)BT * p.in_features * 2 + (size_t)rb * slices * BT * 4 + (size_t)rb * BT * 4;
+  if (smem > (size_t)di->max_smem_optin - 1024)
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "fused exchange: activation tile + partials do not fit in shared memory");
+  auto kernel = gemv_1x16_kernel<T, BT, 0, kGemv1x16Threads, true>;
+  static SmemMarks marks;
+  if (int rc = ensure_smem(kernel, smem, marks, di)) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemv1x16Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p, pc));
   count_launch();
   return AQLM_B200_OK;
 }
@@ -256,6 +287,7 @@ static int matmat_typed(const aqlm_b200_weight_t* w, const void* input, void* ou
   p.num_codebooks = w->num_codebooks;
   p.partial_f32 = partial ? 1 : 0;
   p.n_seg = 1;
+  p.row_block = 0;
   p.seg_end[0] = p.seg_end[1] = p.seg_end[2] = p.seg_end[3] = p.out_features;
   const size_t out_elt = partial ? 4 : 2;
   // largest pass size whose x tile fits in shared memory
@@ -355,6 +387,7 @@ static int launch_lut(const aqlm_b200_weight_t* w, const void* input, void* outp
   p.n_slabs = L.n_slabs;
   p.rows_per_block = L.rows_per_block;
   p.partial_f32 = (flags & AQLM_B200_FLAG_PARTIAL_F32) ? 1 : 0;
+  p.debug = tun().lut_debug;
   constexpr int THREADS = (K <= 2) ? 256 : 512;  // K >= 4: one CTA per SM (128 KiB LUT), so give it 16 warps
   auto kernel = gemv_lut_kernel<T, K, J, THREADS>;
   static SmemMarks marks;
@@ -825,6 +858,7 @@ int aqlm_b200_matmat_grouped(const aqlm_b200_weight_t* w, const int64_t* seg_row
   p.batch = (int)batch;
   p.partial_f32 = partial ? 1 : 0;
   p.n_seg = n_seg;
+  p.row_block = 0;
   int64_t acc = 0;
   for (int i = 0; i < 4; ++i) {
     if (i < n_seg) acc += seg_rows[i];
@@ -1042,6 +1076,65 @@ int aqlm_b200_allreduce_scale_bias(aqlm_b200_comm* c, const float* partial, cons
   else AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, peer_allreduce_epilogue_kernel<__nv_bfloat16>, p));
   count_launch();
   return AQLM_B200_OK;
+}
+
+int aqlm_b200_matmat_allreduce(aqlm_b200_comm* c, const aqlm_b200_weight_t* w, const int64_t* seg_rows, int n_seg,
+                               const void* input, void* output, int64_t batch, void* stream) {
+  if (!c) return fail(AQLM_B200_ERR_SHAPE, "communicator is NULL");
+  int rc = validate(w, true);
+  if (rc) return rc;
+  if (w->num_codebooks != 1 || w->nbits_per_codebook != 16 || w->in_group_size != 8)
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "fused GEMV + exchange is implemented for the 1x16 (in_group 8) scheme");
+  if (batch < 1 || batch > 8) return fail(AQLM_B200_ERR_UNSUPPORTED, "fused GEMV + exchange takes 1..8 batch rows");
+  if (n_seg < 1 || n_seg > 4 || (n_seg > 1 && !seg_rows)) return fail(AQLM_B200_ERR_SHAPE, "1..4 segments");
+  if (!input || !output) return fail(AQLM_B200_ERR_SHAPE, "input/output pointer is NULL");
+  if ((w->out_features & 3) || batch * w->out_features > c->max_elems)
+    return fail(AQLM_B200_ERR_SHAPE, "fused exchange: out_features %% 4 != 0 or batch*out_features exceeds the communicator's %lld",
+                c->max_elems);
+  const size_t row_bytes = (size_t)(w->in_features / 8) * 2;
+  if (row_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(w->codes) & 15) || (reinterpret_cast<uintptr_t>(input) & 15))
+    return fail(AQLM_B200_ERR_UNSUPPORTED, "fused exchange needs 16-byte aligned code rows and input");
+  const DeviceInfo* di = device_info();
+  if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
+  GemvParams p;
+  p.codes = w->codes;
+  p.codebooks = w->codebooks;
+  p.scales = w->scales;
+  p.bias = w->bias;
+  p.x = input;
+  p.y = output;
+  p.out_features = (int)w->out_features;
+  p.in_features = (int)w->in_features;
+  p.in_groups = (int)(w->in_features / 8);
+  p.nbits = 16;
+  p.num_codebooks = 1;
+  p.batch = (int)batch;
+  p.partial_f32 = 0;
+  p.n_seg = n_seg;
+  p.row_block = 0;
+  int64_t acc = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (i < n_seg) acc += (n_seg > 1 ? seg_rows[i] : w->out_features);
+    p.seg_end[i] = (int)acc;
+  }
+  if (acc != w->out_features) return fail(AQLM_B200_ERR_SHAPE, "segment rows do not add up to out_features");
+  GemvPeer pc;
+  for (int r = 0; r < 16; ++r) pc.peer_base[r] = r < c->world ? c->peer_base[r] : nullptr;
+  pc.step = c->local_state;
+  pc.tickets = c->local_state + 1;
+  pc.max_elems = c->max_elems;
+  pc.rank = c->rank;
+  pc.world = c->world;
+  pc.flag_stride = kPeerFlagStride;
+  pc.flag_bytes = kPeerFlagBytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int bt = batch == 1 ? 1 : (batch == 2 ? 2 : (batch <= 4 ? 4 : 8));
+#define AQLM_PEER(T)                                                                                    \
+  (bt == 1 ? launch_1x16_peer<T, 1>(p, pc, di, st) : bt == 2 ? launch_1x16_peer<T, 2>(p, pc, di, st) \
+           : bt == 4 ? launch_1x16_peer<T, 4>(p, pc, di, st) : launch_1x16_peer<T, 8>(p, pc, di, st))
+  if (w->dtype == AQLM_B200_F16) return AQLM_PEER(__half);
+  return AQLM_PEER(__nv_bfloat16);
+#undef AQLM_PEER
 }
 
 int aqlm_b200_matmat_host(const aqlm_b200_weight_t* w, const void* input_host, void* output_host, void* input_dev,

@@ -31,6 +31,20 @@ struct GemvParams {
   // uses the codebook at codebooks + i * (K << nbits) * g elements.  n_seg == 1 for a plain linear.
   int n_seg;
   int seg_end[4];
+  // rows per CTA when every CTA owns ONE CONTIGUOUS block of rows (0: rows dealt round-robin).  The fused exchange needs
+  // contiguous blocks so that a CTA's partials travel as 16-byte vectors.
+  int row_block;
+};
+
+// Peer-memory exchange fused into the GEMV (in_features-sharded path): see gemv_1x16_kernel<..., PEER = true>.
+struct GemvPeer {
+  uint8_t* peer_base[16];  // every rank's shared buffer as mapped in this process (flags, then [set][src rank][max_elems] floats)
+  unsigned int* step;      // local: steps completed (advanced by the last CTA)
+  unsigned int* tickets;   // local: [2], zero on entry, left zero
+  long long max_elems;
+  int rank, world;
+  int flag_stride;         // flags per source rank
+  int flag_bytes;          // size of the flag region at the head of each shared buffer
 };
 
 constexpr int kGemvThreads = 256;  // generic (fallback) kernel
@@ -201,20 +215,33 @@ __global__ void __launch_bounds__(THREADS, 1) gemv_vec_kernel(const GemvParams p
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGemv1x16Threads = 512;
 
-template <typename T, int BT, int GM, int THREADS = kGemv1x16Threads>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS) gemv_1x16_kernel(const GemvParams p) {
+// PEER = true (in_features-sharded multi-GPU path): the kernel's own reduction epilogue performs the ONE exchange of the
+// linear over NVLink peer memory, so a sharded linear is ONE launch and the partials never round-trip through HBM:
+//   every CTA owns a contiguous block of output rows (the same block on every rank); after the fixed-order slice sum it
+//   (A) pushes its fp32 partials into slot [set][my rank] of EVERY rank's buffer with 16-byte P2P stores, (B) publishes
+//   flag[my rank][cta] = step on every rank (st.release.sys, cumulative over the CTA's stores through the barrier),
+//   (C) waits for the W flags of ITS OWN block (ld.acquire.sys) -- CTA c only ever waits for CTA c of the other ranks --
+//   (D) adds the W partial vectors in rank order (deterministic) and applies scale + bias.
+// Two buffer sets alternate by step parity; `step` is read after griddepcontrol.wait (the previous launch, which
+// advances it, has completed).  The grid is one CTA per SM, all co-resident, so the cross-rank wait cannot deadlock.
+template <typename T, int BT, int GM, int THREADS = kGemv1x16Threads, bool PEER = false>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) gemv_1x16_kernel(const GemvParams p, const GemvPeer pc) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int kWarps = THREADS / 32;
   const int upr = p.in_features >> 3;
   griddep_launch_dependents();
-  if ((int)blockIdx.x >= p.out_features) return;
+  if (!PEER && (int)blockIdx.x >= p.out_features) return;  // (a PEER CTA without rows still takes part in the step count)
 
   uint4* sx = reinterpret_cast<uint4*>(smem_raw);
   float* spart = reinterpret_cast<float*>(sx + BT * upr);  // [rows_cta][slices][BT]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunks = p.in_groups >> 3;
   const int slices = (chunks + kSliceChunks - 1) / kSliceChunks;
-  const int rows_cta = (p.out_features - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // row ownership: round-robin (row = cta + i*grid) or one contiguous block per CTA (row = cta*row_block + i)
+  const int row_first = p.row_block ? (int)blockIdx.x * p.row_block : (int)blockIdx.x;
+  const int row_step = p.row_block ? 1 : (int)gridDim.x;
+  const int rows_cta = p.row_block ? max(0, min(p.row_block, p.out_features - row_first))
+                                   : (p.out_features - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tasks = rows_cta * slices;
   const size_t row_bytes = (size_t)p.in_groups * 2;
   const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
@@ -224,13 +251,13 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) gemv_1x16_kernel(const
     const int c = (t - ri * slices) * kSliceChunks + lane;
     live = (t < tasks) && (c < chunks);
     if (!live) return make_uint4(0, 0, 0, 0);
-    const int row = (int)blockIdx.x + ri * (int)gridDim.x;
+    const int row = row_first + ri * row_step;
     return ld_stream_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.codes) + row * row_bytes) + c);
   };
   // codebook of the segment that owns task t's row (grouped launches stack one 1 MiB codebook per segment)
   auto task_codebook = [&](int t) -> const uint4* {
     if (p.n_seg <= 1) return gcb;
-    const int row = (int)blockIdx.x + (t / slices) * (int)gridDim.x;
+    const int row = row_first + (t / slices) * row_step;
     int seg = 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) seg += (i < p.n_seg - 1 && row >= p.seg_end[i]) ? 1 : 0;
@@ -299,19 +326,84 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) gemv_1x16_kernel(const
   }
   __syncthreads();
 
-  for (int i = tid; i < rows_cta * BT; i += THREADS) {
-    const int ri = i / BT;
-    const int b = i - ri * BT;
-    if (b >= p.batch) continue;
-    const int row = (int)blockIdx.x + ri * (int)gridDim.x;
-    float v = 0.f;
-    for (int sl = 0; sl < slices; ++sl) v += spart[((size_t)ri * slices + sl) * BT + b];
-    if (p.partial_f32) {
-      reinterpret_cast<float*>(p.y)[(size_t)b * p.out_features + row] = v;
-    } else {
-      const float s = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+  if constexpr (!PEER) {
+    for (int i = tid; i < rows_cta * BT; i += THREADS) {
+      const int ri = i / BT;
+      const int b = i - ri * BT;
+      if (b >= p.batch) continue;
+      const int row = row_first + ri * row_step;
+      float v = 0.f;
+      for (int sl = 0; sl < slices; ++sl) v += spart[((size_t)ri * slices + sl) * BT + b];
+      if (p.partial_f32) {
+        reinterpret_cast<float*>(p.y)[(size_t)b * p.out_features + row] = v;
+      } else {
+        const float s = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+        const float bv = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
+        reinterpret_cast<T*>(p.y)[(size_t)b * p.out_features + row] = DT<T>::from_float(fmaf(v, s, bv));
+      }
+    }
+  } else {
+    // ---- fused exchange.  sout[b][ri] (fp32) lives behind spart; row_block % 4 == 0 so a block is whole float4s ----
+    float* sout = spart + (size_t)p.row_block * slices * BT;
+    const int RB = p.row_block;
+    for (int i = tid; i < RB * BT; i += THREADS) {
+      const int b = i / RB, ri = i - b * RB;
+      float v = 0.f;
+      if (ri < rows_cta && b < p.batch)
+        for (int sl = 0; sl < slices; ++sl) v += spart[((size_t)ri * slices + sl) * BT + b];
+      sout[i] = v;
+    }
+    __syncthreads();
+    const unsigned int s = *pc.step + 1u;  // read after griddep_wait(): the launch that advances it has completed
+    const int set = (int)(s & 1u);
+    auto slot = [&](int dst, int src) -> float* {
+      return reinterpret_cast<float*>(pc.peer_base[dst] + pc.flag_bytes) + ((long long)set * pc.world + src) * pc.max_elems;
+    };
+    const int nv = rows_cta > 0 ? (RB >> 2) : 0;  // float4s per batch row of this CTA's block (the tail block may be padded)
+    // (A) push my block into every rank's slot [set][my rank]
+    for (int i = tid; i < nv * p.batch * pc.world; i += THREADS) {
+      const int r = i / (nv * p.batch);
+      const int j = i - r * (nv * p.batch);
+      const int b = j / nv, q = j - b * nv;
+      const int row = row_first + 4 * q;
+      if (row < p.out_features) {  // out_features % 4 == 0: a float4 never straddles the end
+        const float4 v = *reinterpret_cast<const float4*>(sout + b * RB + 4 * q);
+        *reinterpret_cast<float4*>(slot(r, pc.rank) + (size_t)b * p.out_features + row) = v;
+      }
+    }
+    // (B) + (C)
+    __syncthreads();
+    if (tid < pc.world) {
+      const int r = tid;
+      unsigned int* theirs = reinterpret_cast<unsigned int*>(pc.peer_base[r]) + pc.rank * pc.flag_stride + blockIdx.x;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(s) : "memory");
+      const unsigned int* mine = reinterpret_cast<const unsigned int*>(pc.peer_base[pc.rank]) + r * pc.flag_stride + blockIdx.x;
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      } while ((int)(seen - s) < 0);
+    }
+    __syncthreads();
+    // (D) fixed-order sum over source ranks + scale + bias
+    for (int i = tid; i < rows_cta * BT; i += THREADS) {
+      const int b = i / rows_cta, ri = i - b * rows_cta;
+      if (b >= p.batch) continue;
+      const int row = row_first + ri;
+      float acc = 0.f;
+      for (int r = 0; r < pc.world; ++r) acc += __ldcg(slot(pc.rank, r) + (size_t)b * p.out_features + row);
+      const float sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
       const float bv = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
-      reinterpret_cast<T*>(p.y)[(size_t)b * p.out_features + row] = DT<T>::from_float(fmaf(v, s, bv));
+      reinterpret_cast<T*>(p.y)[(size_t)b * p.out_features + row] = DT<T>::from_float(fmaf(acc, sc, bv));
+    }
+    // step bookkeeping: the last CTA to finish advances the local step counter
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int old = atomicAdd(pc.tickets, 1u);
+      if (old == gridDim.x - 1) {
+        pc.tickets[0] = 0u;
+        __threadfence();
+        *pc.step = s;
+      }
     }
   }
 }

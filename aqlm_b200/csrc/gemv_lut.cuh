@@ -34,6 +34,7 @@ struct LutParams {
   int n_slabs;
   int rows_per_block;  // multiple of 32
   int partial_f32;
+  int debug;           // experiments: bit0 skip the lookup phase, bit1 skip the LUT build, bit2 skip partials + fix-up
 };
 
 
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kLutThreads, (kLutThreads == 256) ? 2 : 1) gem
   griddep_wait();  // x is produced by the previous kernel
 
   // ---------------- LUT build: D[16 entries x 8 groups] = CB[16 x 8] . X^T[8 x 8], tensor cores ----------------
-  {
+  if (!(p.debug & 2)) {
     // column (2m'+i) of n-tile t holds group (2*NT)*m' + 2t + i, so a lane ends up with 2*NT consecutive groups
     uint32_t bfrag[NT];
 #pragma unroll
@@ -198,10 +199,13 @@ __global__ void __launch_bounds__(kLutThreads, (kLutThreads == 256) ? 2 : 1) gem
     const int row = rbase + jj * RPW + rsub;
     if (row < row_end) part[row] = v[0];
   };
-  for (; r0 < row_end; r0 += 2 * kBatchStride) {
-    process(r0, cwa);
-    if (r0 + kBatchStride < row_end) process(r0 + kBatchStride, cwb);
+  if (!(p.debug & 1)) {
+    for (; r0 < row_end; r0 += 2 * kBatchStride) {
+      process(r0, cwa);
+      if (r0 + kBatchStride < row_end) process(r0 + kBatchStride, cwb);
+    }
   }
+  if (p.debug & 4) return;
 
   // ---------------- fix-up: the last slab CTA of this row block adds the slabs in order ----------------
   __threadfence();

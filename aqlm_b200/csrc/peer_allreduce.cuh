@@ -16,8 +16,9 @@
 namespace aqlm_b200 {
 
 constexpr int kPeerMaxWorld = 16;
-constexpr int kPeerMaxCtas = 16;
-constexpr int kPeerFlagBytes = kPeerMaxWorld * kPeerMaxCtas * 4;  // flag[src rank][cta slice]
+constexpr int kPeerMaxCtas = 16;     // CTAs of the stand-alone exchange kernel below
+constexpr int kPeerFlagStride = 256; // flags per source rank: one per CTA of the FUSED GEMV+exchange kernel (grid = SM count)
+constexpr int kPeerFlagBytes = kPeerMaxWorld * kPeerFlagStride * 4;  // flag[src rank][cta]
 constexpr int kPeerThreads = 512;
 
 struct PeerParams {
@@ -76,8 +77,8 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_epilogue_kernel(c
   __syncthreads();
   if ((int)threadIdx.x < p.world) {
     const int r = threadIdx.x;
-    st_release_sys_u32(reinterpret_cast<unsigned int*>(p.peer_base[r]) + p.rank * kPeerMaxCtas + blockIdx.x, s);
-    const unsigned int* f = reinterpret_cast<const unsigned int*>(p.peer_base[p.rank]) + r * kPeerMaxCtas + blockIdx.x;
+    st_release_sys_u32(reinterpret_cast<unsigned int*>(p.peer_base[r]) + p.rank * kPeerFlagStride + blockIdx.x, s);
+    const unsigned int* f = reinterpret_cast<const unsigned int*>(p.peer_base[p.rank]) + r * kPeerFlagStride + blockIdx.x;
     while ((int)(ld_acquire_sys_u32(f) - s) < 0) {
     }
   }

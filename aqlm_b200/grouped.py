@@ -111,6 +111,13 @@ class ShardedQuantizedLinearGroup(nn.Module):
         from .inference_kernels import cuda_kernel
 
         flat = input.reshape(-1, local)
+        if self.world_size > 1 and self.peer_comm is not None and getattr(self.members[0], "fused_exchange", True):
+            # ONE kernel for the whole group: grouped GEMV + NVLink exchange + scale/bias
+            y = self.peer_comm.matmat_allreduce(flat, self._fused_codes, self._fused_codebooks, self._fused_scales,
+                                                self._fused_bias, self.seg_rows)
+            if y is not None:
+                y = y.reshape(input.shape[:-1] + (sum(self.seg_rows),))
+                return tuple(torch.split(y, self.seg_rows, dim=-1))
         partial = cuda_kernel.matmat_grouped(flat, self._fused_codes, self._fused_codebooks, None, None, self.seg_rows,
                                              partial=True)
         if self.world_size > 1 and self.peer_comm is not None:

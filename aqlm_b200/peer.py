@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import _cabi
-from .inference_kernels.cuda_kernel import _DTYPES, _on_device, _require_cuda, _stream_ptr
+from .inference_kernels.cuda_kernel import _DTYPES, _on_device, _require_cuda, _stream_ptr, make_weight
 
 
 class PeerComm:
@@ -61,3 +61,29 @@ class PeerComm:
                 bias.data_ptr() if bias is not None else None, out.data_ptr(), batch, out_features, _DTYPES[dtype],
                 _stream_ptr(device)))
         return out
+
+    def matmat_allreduce(self, input: torch.Tensor, codes: torch.Tensor, codebooks: torch.Tensor, scales: torch.Tensor,
+                         bias: Optional[torch.Tensor], seg_rows=None) -> Optional[torch.Tensor]:
+        """The sharded linear as ONE kernel (1x16 / in_group 8, <= 8 rows): GEMV on this rank's shard whose epilogue does the
+        exchange over peer memory and applies scale + bias (`aqlm_b200_matmat_allreduce`).  `codebooks` is the member's
+        [1, 65536, 1, 8] tensor, or the [n_seg, 1, 65536, 1, 8] stack of a grouped launch with `seg_rows`.  Returns None when
+        the fused kernel does not cover the case (the caller then runs GEMV + exchange as two launches)."""
+        device = _require_cuda(input, codes, codebooks, scales, bias)
+        cb0 = codebooks[0] if codebooks.dim() == 5 else codebooks
+        n_seg = codebooks.shape[0] if codebooks.dim() == 5 else 1
+        if tuple(cb0.shape) != (1, 65536, 1, 8) or input.dtype not in _DTYPES:
+            return None
+        flat = input.reshape(-1, input.shape[-1])
+        if not flat.is_contiguous():
+            flat = flat.contiguous()
+        batch = flat.shape[0]
+        w = make_weight(codes, cb0, scales.reshape(-1), bias)
+        if batch < 1 or batch > 8 or w.out_features % 4 or batch * w.out_features > self.max_elems or \
+                (w.in_features // 8 * 2) % 16 or flat.shape[1] != w.in_features:
+            return None
+        out = torch.empty((batch, w.out_features), dtype=input.dtype, device=device)
+        seg = (ctypes.c_int64 * n_seg)(*[int(r) for r in seg_rows]) if n_seg > 1 else None
+        with _on_device(device):
+            _cabi.check(_cabi.lib().aqlm_b200_matmat_allreduce(self._comm, ctypes.byref(w), seg, n_seg, flat.data_ptr(),
+                                                               out.data_ptr(), batch, _stream_ptr(device)))
+        return out.reshape(input.shape[:-1] + (w.out_features,))

@@ -12,6 +12,7 @@ for the CUDA kernels there; the product defaults below are the CUDA kernels and 
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -65,6 +66,8 @@ class ShardedQuantizedLinear(nn.Module):
         self._epilogue_fn = epilogue_fn
         # optional aqlm_b200.peer.PeerComm: the all-reduce + epilogue then run as ONE kernel over NVLink peer memory
         self.peer_comm = peer_comm
+        # with a peer communicator: run GEMV + exchange + epilogue as ONE kernel when the scheme allows (1x16)
+        self.fused_exchange = os.environ.get("AQLM_B200_FUSED_EXCHANGE", "1") != "0"
 
     @classmethod
     def from_full(cls, codes, codebooks, scales, bias, process_group=None, rank=None, world_size=None, **kw):
@@ -84,12 +87,14 @@ class ShardedQuantizedLinear(nn.Module):
         if self._partial_fn is None or self._epilogue_fn is None:
             from .inference_kernels import cuda_kernel
 
+            self._default_fns = self._partial_fn is None and self._epilogue_fn is None
             self._partial_fn = self._partial_fn or cuda_kernel.matmat_partial
             self._epilogue_fn = self._epilogue_fn or cuda_kernel.scale_bias
         return self._partial_fn, self._epilogue_fn
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         """`input` is either the full [..., in_features] activation or this rank's [..., in_features/W] slice."""
+        injected = self._partial_fn is not None and not getattr(self, "_default_fns", False)
         partial_fn, epilogue_fn = self._compute_fns()
         local = self.in_end - self.in_begin
         if input.shape[-1] == self.in_features and self.world_size > 1:
@@ -97,6 +102,11 @@ class ShardedQuantizedLinear(nn.Module):
         elif input.shape[-1] != local:
             raise ValueError(f"input has {input.shape[-1]} features; expected {self.in_features} or {local}")
         flat = input.reshape(-1, local)
+        if self.world_size > 1 and self.peer_comm is not None and self.fused_exchange and not injected:
+            # ONE kernel: GEMV + NVLink exchange + scale/bias (1x16, <= 8 rows); None when the case is not covered
+            y = self.peer_comm.matmat_allreduce(flat, self.codes, self.codebooks, self.scales, self.bias)
+            if y is not None:
+                return y.reshape(input.shape[:-1] + (self.out_features,))
         partial = partial_fn(flat, self.codes, self.codebooks)  # [batch, out] fp32, unscaled
         if self.world_size > 1 and self.peer_comm is not None:
             out = self.peer_comm.allreduce_scale_bias(partial, self.scales, self.bias, input.dtype)  # the ONE exchange

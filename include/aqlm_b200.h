@@ -142,6 +142,15 @@ int aqlm_b200_comm_destroy(aqlm_b200_comm* comm);
 int aqlm_b200_allreduce_scale_bias(aqlm_b200_comm* comm, const float* partial, const void* scales, const void* bias,
                                    void* output, int64_t batch, int64_t out_features, int32_t dtype, void* stream);
 
+/* The sharded linear as ONE kernel (1x16, in_group 8, batch <= 8): fused code-gather + dequant + GEMV on this rank's
+ * in_features shard whose reduction epilogue pushes the fp32 partials to every peer over NVLink (contiguous row blocks,
+ * 16-byte P2P stores), signals / waits per CTA, adds the W partial vectors in rank order and applies scale + bias.  `w`
+ * describes the SHARD (in_features = local slice) with full-length scales/bias; `seg_rows`/`n_seg` as in
+ * aqlm_b200_matmat_grouped (n_seg == 1: a plain linear, seg_rows may be NULL).  Every rank must call it the same number
+ * of times in the same order (it shares the step counter with aqlm_b200_allreduce_scale_bias). */
+int aqlm_b200_matmat_allreduce(aqlm_b200_comm* comm, const aqlm_b200_weight_t* w, const int64_t* seg_rows, int n_seg,
+                               const void* input, void* output, int64_t batch, void* stream);
+
 /* End-to-end variant with HOST buffers (pinned): H2D copy of `input_host` into `input_dev`, the fused
  * matmat, D2H copy of the result into `output_host`, and a stream synchronize.  `input_dev`/`output_dev`
  * are caller-owned device scratch of batch*in_features / batch*out_features elements. */
