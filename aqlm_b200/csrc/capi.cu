@@ -435,7 +435,18 @@ static tmap_encode_fn get_tmap_encode() {
   return fn;
 }
 
-constexpr int kGemmMaxTiles = 16384;
+// cuTensorMapEncodeTiled is a DRIVER entry point: it needs a current context on the calling thread.  Threads that have
+// only made runtime calls that do not bind one (e.g. an autograd worker thread: error 201, CUDA_ERROR_INVALID_CONTEXT)
+// get the primary context bound by a no-op runtime call, once per thread.
+static void ensure_driver_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    (void)cudaFree(nullptr);
+    bound = true;
+  }
+}
+
+constexpr int kGemmMaxTiles = 8192;  // split-K tickets use counter words [0, 8192); the LUT GEMV's words follow
 
 struct GemmPlan {
   bool ok = false;       // tcgen05 path applicable
@@ -539,6 +550,7 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   if (!di) return AQLM_B200_ERR_CUDA;
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc) return fail(AQLM_B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  ensure_driver_context();
   CUtensorMap tx, tc;
   {
     cuuint64_t dims[2] = {(cuuint64_t)w->in_features, (cuuint64_t)batch};
@@ -694,6 +706,7 @@ static int launch_gemm_t(const aqlm_b200_weight_t* w, const void* grad_output, v
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc) return fail(AQLM_B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   constexpr int GBT = 16 * K * CB;
+  ensure_driver_context();
   CUtensorMap tg, tc;
   {
     cuuint64_t dims[2] = {(cuuint64_t)w->out_features, (cuuint64_t)batch};

@@ -29,10 +29,12 @@ def _worker(rank, world, port, ret):
             t = to_torch(case, f"cuda:{rank}")
             m = ShardedQuantizedLinear.from_full(t["codes"], t["codebooks"], t["scales"], t["bias"], rank=rank,
                                                  world_size=world, peer_comm=comm)
-            for _ in range(3):  # repeated calls exercise the step counter / buffer-set alternation
-                y = m(t["x"])
-            torch.cuda.synchronize()
-            errs.append(O.relative_error(y.float().cpu().numpy(), oracle_output(case)))
+            for fused in (True, False):  # ONE kernel (GEMV + exchange) and the two-kernel form share the step counter
+                m.fused_exchange = fused
+                for _ in range(3):  # repeated calls exercise the step counter / buffer-set alternation
+                    y = m(t["x"])
+                torch.cuda.synchronize()
+                errs.append(O.relative_error(y.float().cpu().numpy(), oracle_output(case)))
         # grouped: three linears sharing x -> ONE GEMV launch + ONE fused exchange
         from aqlm_b200.grouped import ShardedQuantizedLinearGroup
 
@@ -47,11 +49,30 @@ def _worker(rank, world, port, ret):
         grp = ShardedQuantizedLinearGroup(ms)
         assert grp.fused
         x = to_torch(cases[0], f"cuda:{rank}")["x"]
-        for _ in range(2):
-            ys = grp(x)
+        for fused in (True, False):
+            for mm in ms:
+                mm.fused_exchange = fused
+            for _ in range(2):
+                ys = grp(x)
+            torch.cuda.synchronize()
+            for c, y in zip(cases, ys):
+                errs.append(O.relative_error(y.float().cpu().numpy(), oracle_output(c)))
+        # a BASELINE configs[4] shard shape (Llama-3-70B o_proj, 8192 -> 8192) through the fused kernel, inside a CUDA graph
+        from helpers import c_oracle_check, gpu_case
+
+        t = gpu_case(8192, 8192, 1, 16, 1, seed=77, device=f"cuda:{rank}")  # same seed on every rank: identical full tensors
+        m = ShardedQuantizedLinear.from_full(t["codes"], t["codebooks"], t["scales"], None, rank=rank, world_size=world,
+                                             peer_comm=comm)
+        y = m(t["x"])
         torch.cuda.synchronize()
-        for c, y in zip(cases, ys):
-            errs.append(O.relative_error(y.float().cpu().numpy(), oracle_output(c)))
+        dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = m(t["x"])
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        errs.append(c_oracle_check(t, y))
         ret[rank] = errs
     finally:
         dist.barrier()
@@ -71,3 +92,20 @@ def test_peer_allreduce_two_gpus():
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     for r in range(2):
         assert all(e < 5e-4 for e in ret[r]), (r, ret[r])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_one_process_two_devices_opt_in_shared_memory():
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device; a process that drives several GPUs
+    (HF device_map='auto') must configure every one of them -- kernels needing > 48 KiB must work on cuda:1 after cuda:0."""
+    from helpers import c_oracle_check, gpu_case
+
+    from aqlm_b200.inference_kernels import cuda_kernel
+
+    for dev in ("cuda:0", "cuda:1"):
+        for K, nbits, batch in ((2, 8, 1), (1, 16, 64), (1, 16, 5)):  # LUT GEMV, tcgen05 GEMM, batched gather GEMV
+            t = gpu_case(4096, 4096, K, nbits, batch, seed=K + batch, device=dev)
+            op = cuda_kernel.matmat_dequant if batch > 6 else cuda_kernel.matmat
+            y = op(t["x"], t["codes"], t["codebooks"], t["scales"], None)
+            torch.cuda.synchronize(dev)
+            assert c_oracle_check(t, y) < 5e-4, (dev, K, nbits, batch)
