@@ -57,7 +57,7 @@ static int env_int(const char* name, int dflt) {
 // calls aqlm_b200_reload_tunables() after changing the environment.  Defaults are the shipped configuration.
 struct Tunables {
   int pdl, gemv_ctas_per_sm, gemv_threads, gather_mode, gemv_v2, force_generic;
-  int disable_lut, lut_ctas_per_sm, lut_debug;
+  int disable_lut, lut_ctas_per_sm, lut_debug, lut_cluster, lut_batch_loop;
   int disable_tcgen05, gemm_stages, gemm_ksplit, gemm_cluster, gemm_debug, gemm_gather_mode, gemm_v2, gemm_tile_m, gemm_atmem;
   void load() {
     pdl = env_int("AQLM_B200_PDL", 1);
@@ -69,12 +69,14 @@ struct Tunables {
     disable_lut = env_int("AQLM_B200_DISABLE_LUT", 0);
     lut_ctas_per_sm = env_int("AQLM_B200_LUT_CTAS_PER_SM", 2);  // 128 regs x 256 threads: registers allow 2
     lut_debug = env_int("AQLM_B200_LUT_DEBUG", 0);
+    lut_batch_loop = env_int("AQLM_B200_LUT_BATCH_LOOP", 1);  // batch 2-3 on 256-entry codebooks: one LUT launch per row
+    lut_cluster = env_int("AQLM_B200_LUT_CLUSTER", 1);  // K <= 2, in <= 4096: slab CTAs form a cluster, DSMEM reduction
     disable_tcgen05 = env_int("AQLM_B200_DISABLE_TCGEN05", 0);
     gemm_stages = env_int("AQLM_B200_GEMM_STAGES", 0);
     gemm_ksplit = env_int("AQLM_B200_GEMM_KSPLIT", 0);
-    gemm_cluster = env_int("AQLM_B200_GEMM_CLUSTER", 1);  // measured: no gain, kept for experiments
+    gemm_cluster = env_int("AQLM_B200_GEMM_CLUSTER", 0);  // 0: per plan (pairs of CTAs multicast the X tile: 52.7 vs 55.1 us at 4096->14336 bs=256; 4 is slower)
     gemm_debug = env_int("AQLM_B200_GEMM_DEBUG", 0);
-    gemm_gather_mode = env_int("AQLM_B200_GEMM_GATHER_MODE", 1);  // ld.global.cg: do not allocate gather lines in the small L1
+    gemm_gather_mode = env_int("AQLM_B200_GEMM_GATHER_MODE", -1);  // -1: per scheme (1x16: ld.global.cg, no L1 allocation of the 1 MiB codebook's lines; 256-entry codebooks: L1-resident)
     gemm_v2 = env_int("AQLM_B200_GEMM_V2", -1);                   // -1: per-scheme default
     gemm_tile_m = env_int("AQLM_B200_GEMM_TILE_M", 0);            // 0: chosen by the plan
     gemm_atmem = env_int("AQLM_B200_GEMM_ATMEM", -1);             // A operand in tensor memory; -1: per-scheme default
@@ -337,7 +339,8 @@ struct LutPlan {
   int J = 32, n_slabs = 0, row_blocks = 0, rows_per_block = 0;
   size_t smem = 0, partials_bytes = 0;
 };
-constexpr size_t kWsCountersBytes = 65536;  // fixed counter region at the head of every workspace (16384 tickets)
+constexpr size_t kWsCountersBytes = 65536;  // fixed counter region at the head of every workspace (16384 words)
+constexpr int kGemmMaxTiles = 8192;  // split-K / LUT tickets use counter words [0, 8192); the LUT GEMV's generation words follow
 
 static LutPlan lut_plan(const aqlm_b200_weight_t* w, int64_t batch, const DeviceInfo* di) {
   LutPlan L;
@@ -362,7 +365,7 @@ static LutPlan lut_plan(const aqlm_b200_weight_t* w, int64_t batch, const Device
   rpb = (rpb + 31) / 32 * 32;
   L.rows_per_block = rpb;
   L.row_blocks = (int)((w->out_features + rpb - 1) / rpb);
-  if ((size_t)L.row_blocks * 4 > kWsCountersBytes) return L;
+  if ((size_t)L.row_blocks > (size_t)kGemmMaxTiles) return L;  // tickets in words [0, 8192), generation words above
   L.partials_bytes = (size_t)L.n_slabs * w->out_features * 4;
   L.ok = true;
   return L;
@@ -381,6 +384,7 @@ static int launch_lut(const aqlm_b200_weight_t* w, const void* input, void* outp
   p.x = input;
   p.y = output;
   p.ws_counters = reinterpret_cast<unsigned int*>(workspace);
+  p.ws_gen = p.ws_counters + kGemmMaxTiles;  // generation words live in the upper half of the counter region
   p.ws_partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kWsCountersBytes);
   p.out_features = (int)w->out_features;
   p.in_groups = (int)(w->in_features / 8);
@@ -418,6 +422,89 @@ static int lut_typed(const aqlm_b200_weight_t* w, const void* input, void* outpu
   }
 }
 
+// ---- Kx8 LUT GEMV, cluster / DSMEM variant (K <= 2, at most 8 slabs of 64 groups): host side ---------------
+template <typename T, int K>
+static int launch_lut_cluster(const aqlm_b200_weight_t* w, const void* input, void* output, uint32_t flags,
+                              const DeviceInfo* di, cudaStream_t st, bool* taken) {
+  *taken = false;
+  const int in_groups = (int)(w->in_features / 8);
+  const int n_slabs = (in_groups + kLutCJ - 1) / kLutCJ;
+  auto kernel = gemv_lut_cluster_kernel<T, K>;
+  const size_t lut_bytes = (size_t)K * 256 * kLutCJ * 4;
+  // how many clusters of n_slabs CTAs can be resident at once: the grid must be ONE wave (a second wave doubles the time)
+  static std::atomic<int> max_clusters[kMaxDevices][9];
+  int mc = max_clusters[di->index][n_slabs].load(std::memory_order_relaxed);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = n_slabs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.blockDim = dim3(kLutCThreads);
+  cfg.stream = st;
+  static SmemMarks marks;
+  if (mc == 0) {
+    const size_t smem_max = lut_bytes + 8192;
+    if (int rc = ensure_smem(kernel, smem_max, marks, di)) return rc;
+    cfg.gridDim = dim3(n_slabs, di->sm_count);
+    cfg.dynamicSmemBytes = smem_max;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) {
+      (void)cudaGetLastError();
+      n = -1;  // not launchable as a cluster here: use the workspace kernel
+    }
+    mc = n;
+    max_clusters[di->index][n_slabs].store(mc, std::memory_order_relaxed);
+  }
+  if (mc < 1) return AQLM_B200_OK;
+  int rpb = (int)((w->out_features + mc - 1) / mc);
+  rpb = (rpb + 31) / 32 * 32;
+  if (rpb > 2048) return AQLM_B200_OK;  // per-row partials live in shared memory
+  const int row_blocks = (int)((w->out_features + rpb - 1) / rpb);
+  const size_t smem = lut_bytes + (size_t)rpb * 4;
+  if (int rc = ensure_smem(kernel, smem, marks, di)) return rc;
+  LutClusterParams p;
+  p.codes = w->codes;
+  p.codebooks = w->codebooks;
+  p.scales = w->scales;
+  p.bias = w->bias;
+  p.x = input;
+  p.y = output;
+  p.out_features = (int)w->out_features;
+  p.in_groups = in_groups;
+  p.n_slabs = n_slabs;
+  p.rows_per_block = rpb;
+  p.partial_f32 = (flags & AQLM_B200_FLAG_PARTIAL_F32) ? 1 : 0;
+  cfg.gridDim = dim3(n_slabs, row_blocks);
+  cfg.dynamicSmemBytes = smem;
+  cfg.numAttrs = 2;
+  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
+  count_launch();
+  *taken = true;
+  return AQLM_B200_OK;
+}
+
+// Batch-1 call on a 1x8 / 2x8 weight whose in_features fit 8 slabs: no workspace needed.
+static int try_lut_cluster(const aqlm_b200_weight_t* w, const void* input, void* output, int64_t batch, uint32_t flags,
+                           const DeviceInfo* di, cudaStream_t st, bool* taken) {
+  *taken = false;
+  const int K = w->num_codebooks;
+  const int in_groups = (int)(w->in_features / 8);
+  if (batch != 1 || w->nbits_per_codebook != 8 || w->in_group_size != 8 || (K != 1 && K != 2)) return AQLM_B200_OK;
+  if (!tun().lut_cluster || tun().disable_lut || tun().lut_debug) return AQLM_B200_OK;
+  if ((in_groups & 1) || in_groups > 8 * kLutCJ) return AQLM_B200_OK;
+  if ((reinterpret_cast<uintptr_t>(w->codes) & 3) || (reinterpret_cast<uintptr_t>(input) & 3)) return AQLM_B200_OK;
+  if (w->dtype == AQLM_B200_F16)
+    return K == 1 ? launch_lut_cluster<__half, 1>(w, input, output, flags, di, st, taken)
+                  : launch_lut_cluster<__half, 2>(w, input, output, flags, di, st, taken);
+  return K == 1 ? launch_lut_cluster<__nv_bfloat16, 1>(w, input, output, flags, di, st, taken)
+                : launch_lut_cluster<__nv_bfloat16, 2>(w, input, output, flags, di, st, taken);
+}
+
 // ---- fused dequant + tcgen05 GEMM: host side ------------------------------------------------------
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -446,7 +533,6 @@ static void ensure_driver_context() {
   }
 }
 
-constexpr int kGemmMaxTiles = 8192;  // split-K tickets use counter words [0, 8192); the LUT GEMV's words follow
 
 struct GemmPlan {
   bool ok = false;       // tcgen05 path applicable
@@ -489,6 +575,7 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   if (gemm_smem_layout(S, g.n_tile, g.atmem).total > budget) return g;
   const int forced_s = tun().gemm_stages;
   if (forced_s >= 2 && forced_s <= S) S = forced_s;
+  if (forced_s == 4 && g.v2 && gemm_smem_layout(4, g.n_tile, g.atmem).total <= budget) S = 4;  // experiment: 4 producer groups
   g.stages = S;
   // ---- tile height and split-K: a small cost model over (tile_m, ksplit), in SM clocks ----
   //   per k-block of one CTA: max(gathers, tensor pipe, shared-memory traffic) + a fixed synchronisation cost;
@@ -502,9 +589,12 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   int best_tm = kGemmBlockM, best_ks = 1;
   double best = 1e30;
   const int max_ks = !allow_split ? 1 : (g.total_kblocks / 2 < 16 ? (g.total_kblocks / 2 < 1 ? 1 : g.total_kblocks / 2) : 16);
+  const bool want_pairs = (tun().gemm_cluster > 0 ? tun().gemm_cluster : (g.n_tile >= 128 ? 2 : 1)) > 1;
   for (int tm = kGemmBlockM; tm >= 32; tm -= (tm > 64 ? 1 : 8)) {
     const long long tiles = ((w->out_features + tm - 1) / tm) * (long long)g.n_tiles;
     if (tiles > kGemmMaxTiles) continue;
+    // CTA pairs multicast the X tile: keep the number of M tiles even (full-height tiles stay as the fallback)
+    if (want_pairs && tm != kGemmBlockM && (((w->out_features + tm - 1) / tm) & 1)) continue;
     const double t_gather = tm * 8.0 * K / gather_per_clk;
     const double t_smem = (g.atmem ? 0.0 : (128.0 + tm) * 128.0 / 128.0) + 2.0 * g.n_tile;  // bytes / (128 B/clk)
     const double t_kb = (t_gather > t_mma ? (t_gather > t_smem ? t_gather : t_smem) : (t_mma > t_smem ? t_mma : t_smem)) + 60.0;
@@ -535,7 +625,7 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   g.ksplit = ks;
   // X-tile multicast: CTAs of a cluster (consecutive M tiles, same K range) each TMA-load 1/C of the X tile and
   // multicast it to all C, cutting the L2->SM traffic of X by C.
-  int cl = tun().gemm_cluster;
+  int cl = tun().gemm_cluster > 0 ? tun().gemm_cluster : (g.n_tile >= 128 ? 2 : 1);
   while (cl > 1 && (g.m_tiles % cl != 0 || g.n_tile % (8 * cl) != 0)) cl >>= 1;
   g.cluster = cl < 1 ? 1 : cl;
   g.partials_bytes = ks > 1 ? (size_t)g.m_tiles * g.n_tiles * ks * g.n_tile * kGemmBlockM * 4 : 0;
@@ -590,11 +680,11 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   p.tile_m = g.tile_m;
   p.cluster = g.cluster;
   p.debug = tun().gemm_debug;
-  p.gather_mode = tun().gemm_gather_mode;
+  p.gather_mode = tun().gemm_gather_mode >= 0 ? tun().gemm_gather_mode : (w->nbits_per_codebook > 8 ? 1 : 0);
   p.codes = w->codes;
   p.row_bytes = (long long)(w->in_features / 8) * K * CB;
   const size_t smem = gemm_smem_layout(g.stages, g.n_tile, g.atmem).total;
-  const bool v2 = g.v2 && g.stages <= 3;
+  const bool v2 = g.v2 && g.stages <= 4;
   const bool atmem = g.atmem && v2;
   auto kernel = atmem ? gemm_dequant_kernel<T, K, CB, true, true>
                       : (v2 ? gemm_dequant_kernel<T, K, CB, true, false> : gemm_dequant_kernel<T, K, CB, false, false>);
@@ -743,7 +833,7 @@ static int launch_gemm_t(const aqlm_b200_weight_t* w, const void* grad_output, v
   p.ksplit = g.ksplit;
   p.n_tile = g.n_tile;
   p.stages = g.stages;
-  p.gather_mode = tun().gemm_gather_mode;
+  p.gather_mode = tun().gemm_gather_mode >= 0 ? tun().gemm_gather_mode : (w->nbits_per_codebook > 8 ? 1 : 0);
   const size_t smem = gemm_t_smem_layout(g.stages, g.n_tile, GBT).total;
   auto kernel = gemm_dequant_t_kernel<T, K, CB>;
   static SmemMarks marks;
@@ -808,6 +898,21 @@ int aqlm_b200_matmat_ex(const aqlm_b200_weight_t* w, const void* input, void* ou
   const DeviceInfo* di = device_info();
   if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // batch 1 -- and batch 2-3 as one launch per row, like the reference's per-row host loop (cuda_kernel.cpp:387-421):
+    // measured faster than one pass of the gather kernel up to 3 rows (profiles/r02/probe_lut_*.jsonl)
+    const int64_t lut_rows = (batch == 1 || (tun().lut_batch_loop && batch <= 3)) ? batch : 0;
+    const size_t out_elt = partial ? 4 : 2;
+    int64_t done = 0;
+    for (; done < lut_rows; ++done) {
+      bool taken = false;
+      rc = try_lut_cluster(w, reinterpret_cast<const uint8_t*>(input) + (size_t)done * w->in_features * 2,
+                           reinterpret_cast<uint8_t*>(output) + (size_t)done * w->out_features * out_elt, 1, flags, di, st, &taken);
+      if (rc) return rc;
+      if (!taken) break;  // not applicable (decided before any launch: `taken` is the same for every row)
+    }
+    if (lut_rows > 0 && done == lut_rows) return AQLM_B200_OK;
+  }
   if (w->dtype == AQLM_B200_F16) return matmat_typed<__half>(w, input, output, batch, flags, di, st);
   return matmat_typed<__nv_bfloat16>(w, input, output, batch, flags, di, st);
 }
@@ -816,7 +921,8 @@ size_t aqlm_b200_matmat_workspace_bytes(const aqlm_b200_weight_t* w, int64_t bat
   if (validate(w, false) != AQLM_B200_OK || batch <= 0) return 0;
   const DeviceInfo* di = device_info();
   if (!di) return 0;
-  const LutPlan L = lut_plan(w, batch, di);
+  if (batch > 2) return 0;
+  const LutPlan L = lut_plan(w, 1, di);
   return L.ok ? kWsCountersBytes + L.partials_bytes : 0;
 }
 
@@ -825,14 +931,28 @@ int aqlm_b200_matmat_ws(const aqlm_b200_weight_t* w, const void* input, void* ou
   const bool partial = (flags & AQLM_B200_FLAG_PARTIAL_F32) != 0;
   int rc = validate(w, !partial);
   if (rc) return rc;
-  if (batch == 1 && workspace && input && output && (reinterpret_cast<uintptr_t>(input) & 3) == 0) {
+  const int64_t ws_rows = (batch == 1 || (tun().lut_batch_loop && batch == 2 && w->num_codebooks >= 4)) ? batch : 0;
+  if (ws_rows > 0 && workspace && input && output && (reinterpret_cast<uintptr_t>(input) & 3) == 0) {
     const DeviceInfo* di = device_info();
     if (!di) return (int)(strstr(tls_error_buf(), "sm_100a") ? AQLM_B200_ERR_ARCH : AQLM_B200_ERR_CUDA);
-    const LutPlan L = lut_plan(w, batch, di);
-    if (L.ok && workspace_bytes >= kWsCountersBytes + L.partials_bytes) {
-      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-      if (w->dtype == AQLM_B200_F16) return lut_typed<__half>(w, input, output, flags, L, workspace, st);
-      return lut_typed<__nv_bfloat16>(w, input, output, flags, L, workspace, st);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (batch == 1) {  // K <= 2, in <= 4096: the cluster kernel needs no workspace (matmat_ex also loops it for batch 2-3)
+      bool taken = false;
+      rc = try_lut_cluster(w, input, output, 1, flags, di, st, &taken);
+      if (rc || taken) return rc;
+    }
+    const LutPlan L = lut_plan(w, 1, di);
+    const bool cluster_case = w->num_codebooks <= 2 && (w->in_features / 8) <= 8 * kLutCJ && tun().lut_cluster;
+    if (L.ok && workspace_bytes >= kWsCountersBytes + L.partials_bytes && !(batch > 1 && cluster_case)) {
+      const size_t out_elt = partial ? 4 : 2;
+      for (int64_t b = 0; b < ws_rows; ++b) {  // launches are stream-ordered: the workspace is reused row after row
+        const void* xin = reinterpret_cast<const uint8_t*>(input) + (size_t)b * w->in_features * 2;
+        void* yout = reinterpret_cast<uint8_t*>(output) + (size_t)b * w->out_features * out_elt;
+        rc = w->dtype == AQLM_B200_F16 ? lut_typed<__half>(w, xin, yout, flags, L, workspace, st)
+                                       : lut_typed<__nv_bfloat16>(w, xin, yout, flags, L, workspace, st);
+        if (rc) return rc;
+      }
+      return AQLM_B200_OK;
     }
   }
   return aqlm_b200_matmat_ex(w, input, output, batch, flags, stream);

@@ -24,8 +24,8 @@ namespace aqlm_b200 {
 
 constexpr int kGemmProducerWarps = 16;
 constexpr int kGemmThreads = 128 + 32 * kGemmProducerWarps;  // warps 0-3: TMA / MMA / TMEM-alloc, then epilogue; warps 4-19: dequant producers
-// V2 producer mapping: one 4-warp group per smem stage (at most 3 stages), each group owns every S-th k-block entirely
-constexpr int kGemmThreadsV2 = 128 + 32 * 4 * 3;
+// V2 producer mapping: one 4-warp group per smem stage (at most 4 stages), each group owns every S-th k-block entirely
+constexpr int kGemmThreadsV2 = 128 + 32 * 4 * 4;
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;          // 64 halves = 128 bytes = one swizzle row
 constexpr int kCodeTileBytes = 128;      // bytes of codes per row per code tile (TMA box inner extent)

@@ -16,6 +16,8 @@
 //     in a fixed order and applies scale + bias (deterministic, no float atomics).
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace aqlm_b200 {
@@ -28,7 +30,8 @@ struct LutParams {
   const void* x;       // [in_features]
   void* y;             // [out_features] T, or float when partial_f32
   float* ws_partials;  // [n_slabs][out_features]
-  unsigned int* ws_counters;  // [row_blocks], zero on entry, left zero
+  unsigned int* ws_counters;  // [row_blocks] arrival tickets, zero on entry, left zero
+  unsigned int* ws_gen;       // [row_blocks] generation words (monotonic; any value on entry)
   int out_features;
   int in_groups;
   int n_slabs;
@@ -207,29 +210,46 @@ __global__ void __launch_bounds__(kLutThreads, (kLutThreads == 256) ? 2 : 1) gem
   }
   if (p.debug & 4) return;
 
-  // ---------------- fix-up: the last slab CTA of this row block adds the slabs in order ----------------
+  // ---------------- fix-up: ALL slab CTAs of this row block share the cross-slab sum ----------------
+  // The grid is one resident wave (host side guarantees it), so the n_slabs CTAs of a row block can rendezvous: each
+  // publishes its partials, takes a ticket, and the last arrival bumps the block's generation word; everybody then adds
+  // the slabs IN SLAB ORDER (deterministic) for its own 1/n_slabs share of the rows (32-row chunks dealt round-robin).
+  // Before: only the last-arriving CTA did the whole block (n_slabs x rows loads behind one L2 round trip each) --
+  // measured 4.8 us of an 11.8 us kernel at 4096->11008 2x8 and 8.8 of 16.5 us at 11008->4096 (profiles/r02/probe_lut.jsonl).
+  unsigned int* s_gen = reinterpret_cast<unsigned int*>(lut + (size_t)K * 256 * J);
+  if (tid == 0) *s_gen = *reinterpret_cast<volatile unsigned int*>(p.ws_gen + rb);  // cannot advance before I arrive
   __threadfence();
   __syncthreads();
-  unsigned int* s_last = reinterpret_cast<unsigned int*>(lut + (size_t)K * 256 * J);
   if (tid == 0) {
+    const unsigned int g0 = *s_gen;
     const unsigned int old = atomicAdd(p.ws_counters + rb, 1u);
-    *s_last = (old == (unsigned int)p.n_slabs - 1) ? 1u : 0u;
-    if (*s_last) p.ws_counters[rb] = 0u;
+    if (old == (unsigned int)p.n_slabs - 1) {
+      p.ws_counters[rb] = 0u;  // leave the ticket clean for the next call
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ws_gen + rb), "r"(g0 + 1u) : "memory");
+    } else {
+      unsigned int g;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(p.ws_gen + rb) : "memory");
+      } while (g == g0);
+    }
   }
   __syncthreads();
-  if (*s_last) {
-    __threadfence();
-    for (int row = row_begin + tid; row < row_end; row += kLutThreads) {
+  {
+    const int chunks = (row_end - row_begin + 31) >> 5;
+    for (int c = slab + warp * p.n_slabs; c < chunks; c += kWarps * p.n_slabs) {
+      const int row = row_begin + (c << 5) + lane;
+      if (row >= row_end) continue;
       float acc = 0.f;
-      int s = 0;
-      for (; s + 8 <= p.n_slabs; s += 8) {  // 8 independent L2 loads in flight, added in slab order
+      int sidx = 0;
+      for (; sidx + 8 <= p.n_slabs; sidx += 8) {  // 8 independent L2 loads in flight, added in slab order
         float t8[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t8[u] = __ldcg(p.ws_partials + (size_t)(s + u) * p.out_features + row);
+        for (int u = 0; u < 8; ++u) t8[u] = __ldcg(p.ws_partials + (size_t)(sidx + u) * p.out_features + row);
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc += t8[u];
       }
-      for (; s < p.n_slabs; ++s) acc += __ldcg(p.ws_partials + (size_t)s * p.out_features + row);
+      for (; sidx < p.n_slabs; ++sidx) acc += __ldcg(p.ws_partials + (size_t)sidx * p.out_features + row);
       if (p.partial_f32) {
         reinterpret_cast<float*>(p.y)[row] = acc;
       } else {
@@ -239,6 +259,192 @@ __global__ void __launch_bounds__(kLutThreads, (kLutThreads == 256) ? 2 : 1) gem
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cluster variant for K = 1, 2 and in_features <= 8 slabs of 64 groups (4096 for g = 8): the slab CTAs of a row block form
+// ONE thread-block cluster and reduce their partial rows through DISTRIBUTED SHARED MEMORY -- no global partials, no
+// fence/atomic/poll round trips (those cost 3.8 us of an 11 us kernel, profiles/r02/probe_lut_c.jsonl).
+//   * slab = 64 in-groups, LUT [K][256][64] fp32 (64/128 KiB), 512 threads, one CTA per SM;
+//   * a lane owns the ADJACENT groups 2l, 2l+1: one aligned code word per row (K=2: 4 bytes, K=1: 2 bytes) = a fully
+//     coalesced 128/64-byte row segment per warp; group 2l sits at LUT position l, group 2l+1 at position 32+l, so both
+//     lookups of a lane hit bank l (conflict-free) and the row stride is 256 B: byte 1 of the word is already a row offset;
+//   * per-row totals of the slab go to shared memory; after a cluster barrier CTA r adds, IN SLAB ORDER (deterministic),
+//     the n_slabs partial values of every row of its share with ld.shared::cluster, applies scale + bias and writes y.
+// ---------------------------------------------------------------------------------------------------
+struct LutClusterParams {
+  const void* codes;
+  const void* codebooks;
+  const void* scales;
+  const void* bias;
+  const void* x;
+  void* y;
+  int out_features;
+  int in_groups;
+  int n_slabs;         // = cluster size along x
+  int rows_per_block;  // multiple of 32
+  int partial_f32;
+};
+
+constexpr int kLutCJ = 64;
+constexpr int kLutCThreads = 512;
+
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(kLutCThreads, 1) gemv_lut_cluster_kernel(const LutClusterParams p) {
+  static_assert(K == 1 || K == 2, "cluster LUT kernel: one or two 256-entry codebooks");
+  extern __shared__ __align__(16) float lut[];  // [K][256][64], then spart[rows_per_block]
+  constexpr int J = kLutCJ, NT = J / 8, kWarps = kLutCThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slab = blockIdx.x, rb = blockIdx.y;
+  const int j0 = slab * J;
+  griddep_launch_dependents();
+  float* spart = lut + (size_t)K * 256 * J;
+  const int row_begin = rb * p.rows_per_block;
+  const int row_end = min(p.out_features, row_begin + p.rows_per_block);
+  const size_t row_bytes = (size_t)p.in_groups * K;
+  // lane <-> groups (j0 + 2l, j0 + 2l + 1): CW = 2K code bytes per row
+  using CodeWord = typename std::conditional<K == 2, uint32_t, uint16_t>::type;
+  const bool g_ok = j0 + 2 * lane + 1 < p.in_groups;   // (in_groups is even for every shape this kernel accepts)
+  const uint8_t* cbase = reinterpret_cast<const uint8_t*>(p.codes) + (size_t)(j0 + 2 * lane) * K;
+  constexpr int RB = 32;
+  constexpr int kBatchStride = kWarps * RB;
+  auto load_codes = [&](int r0, uint32_t (&cw)[RB]) {
+    const uint8_t* src = cbase + (size_t)r0 * row_bytes;
+    if (g_ok && r0 + RB <= row_end) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i, src += row_bytes) cw[i] = (uint32_t)__ldg(reinterpret_cast<const CodeWord*>(src));
+    } else {
+#pragma unroll
+      for (int i = 0; i < RB; ++i, src += row_bytes) {
+        cw[i] = 0u;
+        if (g_ok && r0 + i < row_end) cw[i] = (uint32_t)__ldg(reinterpret_cast<const CodeWord*>(src));
+      }
+    }
+  };
+  // ---- prologue (weights only; overlaps the previous kernel under PDL) ----
+  uint32_t cwa[RB], cwb[RB];
+  int r0 = row_begin + warp * RB;
+  load_codes(r0, cwa);
+  if (r0 + kBatchStride < row_end) load_codes(r0 + kBatchStride, cwb);
+  constexpr int MT = (K * 16) / kWarps;  // 16-entry tiles per warp
+  static_assert((K * 16) % kWarps == 0, "tiles must divide evenly");
+  const int q = lane >> 2, m = lane & 3;
+  uint32_t afrag[MT][2];
+  {
+    const uint32_t* cb32 = reinterpret_cast<const uint32_t*>(p.codebooks);
+#pragma unroll
+    for (int u = 0; u < MT; ++u) {
+      const int e0 = (warp + u * kWarps) * 16;
+      afrag[u][0] = __ldg(cb32 + (size_t)(e0 + q) * 4 + m);
+      afrag[u][1] = __ldg(cb32 + (size_t)(e0 + q + 8) * 4 + m);
+    }
+  }
+  griddep_wait();  // x is produced by the previous kernel
+  // ---- LUT build (tensor cores): lane (q, m) ends with groups 16m .. 16m+15 of entries e0+q and e0+q+8;
+  //      even groups go to positions 8m + t, odd groups to 32 + 8m + t ----
+  {
+    uint32_t bfrag[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int gg = j0 + 16 * (q >> 1) + 2 * t + (q & 1);
+      bfrag[t] = gg < p.in_groups ? reinterpret_cast<const uint32_t*>(p.x)[gg * 4 + m] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < MT; ++u) {
+      const int e0 = (warp + u * kWarps) * 16;
+      float d[NT][4];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        d[t][0] = d[t][1] = d[t][2] = d[t][3] = 0.f;
+        mma_m16n8k8(d[t], afrag[u][0], afrag[u][1], bfrag[t], DT<T>::is_bf16);
+      }
+      float* ra = lut + (size_t)(e0 + q) * J + 8 * m;
+      float* rb8 = lut + (size_t)(e0 + q + 8) * J + 8 * m;
+      const bool odd = q & 1;  // odd entry rows store their second half first: a quarter-warp then covers all 32 banks
+      // c: which accumulator column (0/1: entry e0+q, even/odd groups; 2/3: entry e0+q+8)
+#define AQLM_LUT_ROW(dst, c)                                                                            \
+      {                                                                                                 \
+        const float4 lo = make_float4(d[0][c], d[1][c], d[2][c], d[3][c]);                              \
+        const float4 hi = make_float4(d[4][c], d[5][c], d[6][c], d[7][c]);                              \
+        *reinterpret_cast<float4*>((dst) + (odd ? 4 : 0)) = odd ? hi : lo;                              \
+        *reinterpret_cast<float4*>((dst) + (odd ? 0 : 4)) = odd ? lo : hi;                              \
+      }
+      AQLM_LUT_ROW(ra, 0)
+      AQLM_LUT_ROW(ra + 32, 1)
+      AQLM_LUT_ROW(rb8, 2)
+      AQLM_LUT_ROW(rb8 + 32, 3)
+#undef AQLM_LUT_ROW
+    }
+  }
+  __syncthreads();
+  // ---- lookups ----
+  const uint32_t lane_off = (uint32_t)lane * 4u;
+  const char* lut_b = reinterpret_cast<const char*>(lut);
+  auto process = [&](int rbase, uint32_t (&cw)[RB]) {
+    float v[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const uint32_t w = cw[i];
+      float acc;
+      if constexpr (K == 2) {  // bytes: [g0 k0][g0 k1][g1 k0][g1 k1]; a LUT row is 256 B
+        acc = *reinterpret_cast<const float*>(lut_b + (((w << 8) & 0xff00u) | lane_off));
+        acc += *reinterpret_cast<const float*>(lut_b + 65536 + ((w & 0xff00u) | lane_off));
+        acc += *reinterpret_cast<const float*>(lut_b + 128 + (((w >> 8) & 0xff00u) | lane_off));
+        acc += *reinterpret_cast<const float*>(lut_b + 65536 + 128 + (((w >> 16) & 0xff00u) | lane_off));
+      } else {                 // bytes: [g0][g1]
+        acc = *reinterpret_cast<const float*>(lut_b + (((w << 8) & 0xff00u) | lane_off));
+        acc += *reinterpret_cast<const float*>(lut_b + 128 + ((w & 0xff00u) | lane_off));
+      }
+      v[i] = acc;
+    }
+    if (rbase + 2 * kBatchStride < row_end) load_codes(rbase + 2 * kBatchStride, cw);
+#pragma unroll
+    for (int dd = 16, n = RB; dd >= 1; dd >>= 1, n >>= 1) {
+      const bool up = (lane & dd) != 0;
+#pragma unroll
+      for (int i = 0; i < n / 2; ++i) {
+        const float send = up ? v[i] : v[i + n / 2];
+        const float keep = up ? v[i + n / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, dd);
+      }
+    }
+    const int row = rbase + lane;
+    if (row < row_end) spart[row - row_begin] = v[0];
+  };
+  for (; r0 < row_end; r0 += 2 * kBatchStride) {
+    process(r0, cwa);
+    if (r0 + kBatchStride < row_end) process(r0 + kBatchStride, cwb);
+  }
+  // ---- cross-slab sum through distributed shared memory ----
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  {
+    const int nrows = row_end - row_begin;
+    const int per = (nrows + p.n_slabs - 1) / p.n_slabs;
+    const int lo = slab * per, hi = min(nrows, lo + per);
+    const uint32_t sp = (uint32_t)__cvta_generic_to_shared(spart);
+    for (int r = lo + tid; r < hi; r += kLutCThreads) {
+      float acc = 0.f;
+      for (int s2 = 0; s2 < p.n_slabs; ++s2) acc += ld_dsmem_f32(sp + 4u * (uint32_t)r, (uint32_t)s2);
+      const int row = row_begin + r;
+      if (p.partial_f32) {
+        reinterpret_cast<float*>(p.y)[row] = acc;
+      } else {
+        const float sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+        const float bi = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
+        reinterpret_cast<T*>(p.y)[row] = DT<T>::from_float(fmaf(acc, sc, bi));
+      }
+    }
+  }
+  // nobody leaves while a peer may still read its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 }  // namespace aqlm_b200

@@ -664,6 +664,67 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     clocks = sampler.stop() if sampler else None
 
+    # ---- N > 1, reported beside the headline: the Megatron-style pairing --------------------------
+    # q/k/v and gate/up sharded along OUT_features (each rank owns rows, no exchange: their consumers are sharded the same
+    # way), o_proj and down_proj sharded along in_features with ONE exchange each: 2 exchanges per layer instead of 4.
+    pairing = None
+    if world > 1 and (K, nbits) == (1, 16) and not args.skip_pairing:
+        try:
+            import aqlm_b200
+            from aqlm_b200.grouped import QuantizedLinearGroup
+            from aqlm_b200.sharded import ShardedQuantizedLinear
+
+            gen = torch.Generator(device=device).manual_seed(4321 + rank)
+            lin = {name: (fin, fout) for name, fin, fout in layer_linears(model)}
+
+            def rows_shard(name):
+                fin, fout = lin[name]
+                m = aqlm_b200.QuantizedLinear(fin, fout // world, 8, 1, K, nbits, bias=False, device=device, dtype=torch.float16)
+                m.codes.data = torch.randint(-32768, 32768, m.codes.shape, dtype=torch.int16, device=device, generator=gen)
+                m.codebooks.data = torch.randn(m.codebooks.shape, dtype=torch.float16, device=device, generator=gen)
+                m.scales.data = (0.75 + 0.5 * torch.rand(m.scales.shape, device=device, generator=gen)).half()
+                return m
+
+            def cols_shard(name):
+                fin, fout = lin[name]
+                m = ShardedQuantizedLinear(fin, fout, 8, 1, K, nbits, bias=False, rank=rank, world_size=world, device=device,
+                                           dtype=torch.float16, peer_comm=peer_comm)
+                m.codes.data = torch.randint(-32768, 32768, m.codes.shape, dtype=torch.int16, device=device, generator=gen)
+                m.codebooks.data = torch.randn(m.codebooks.shape, dtype=torch.float16, device=device, generator=gen)
+                m.scales.data = (0.75 + 0.5 * torch.rand(m.scales.shape, device=device, generator=gen)).half()
+                return m
+
+            h, inter = MODELS[model]["hidden"], MODELS[model]["inter"]
+            pl = []
+            for _ in range(n_layers):
+                pl.append([(QuantizedLinearGroup([rows_shard("q_proj"), rows_shard("k_proj"), rows_shard("v_proj")]), h),
+                           (cols_shard("o_proj"), h // world),
+                           (QuantizedLinearGroup([rows_shard("gate_proj"), rows_shard("up_proj")]), h),
+                           (cols_shard("down_proj"), inter // world)])
+            xs = {n: torch.randn((1, n), dtype=torch.float16, device=device) for n in {n for mods in pl for _, n in mods}}
+
+            def pstep():
+                for mods in pl:
+                    for m, n in mods:
+                        m(xs[n])
+            pstep()
+            torch.cuda.synchronize()
+            gp = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gp):
+                pstep()
+            for _ in range(3):
+                gp.replay()
+            ms_p = timed(gp.replay, max(5, args.steps // 2)) / max(5, args.steps // 2)
+            pairing = {"value": total_bytes / (ms_p * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_p,
+                       "layout": "q/k/v and gate/up sharded along out_features (no exchange), o_proj and down_proj along "
+                                 "in_features with one fused exchange each: 2 exchanges per layer"}
+            gp.reset()
+            del pl, gp, xs
+            torch.cuda.empty_cache()
+        except Exception as e:
+            pairing = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.synchronize()
+
     # single-GPU point of the SAME workload when N > 1: rank 0 alone, unsharded, same grouping, FULL depth (Llama-3-70B
     # 1x16 is 16 GiB of codes: fits beside the shard), so the driver's curve can be read as same-workload strong scaling
     same_n1 = None
@@ -719,7 +780,8 @@ def run_ours(args):
         if os.path.exists(tpath):
             try:
                 with open(tpath) as f:
-                    traffic = json.load(f).get(f"{model}:{K}x{nbits}:bytes_per_launch")
+                    key = f"{model}:{K}x{nbits}:bytes_per_launch" if world == 1 else f"{model}:{K}x{nbits}:n{world}:bytes_per_launch"
+                    traffic = json.load(f).get(key)
             except Exception:
                 traffic = None
         line = {
@@ -758,6 +820,8 @@ def run_ours(args):
                 line["same_workload_scaling_efficiency"] = value / (world * same_n1["value"])
         if parity is not None:
             line["sharded_parity"] = parity
+        if pairing is not None:
+            line["tp_pairing_variant"] = pairing
         print(json.dumps(line), flush=True)
     if world > 1:
         # Clean teardown: drop the CUDA graphs (they may hold captured NCCL kernels), sync, then destroy the process group.
@@ -800,6 +864,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-n1", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true")
+    ap.add_argument("--skip-pairing", action="store_true", help="N>1: skip the out/in-features pairing variant")
     ap.add_argument("--skip-parity", action="store_true", help="N>1: skip the sharded-vs-unsharded correctness pass")
     ap.add_argument("--skip-reference-gpu", action="store_true", help="skip the reference CUDA kernels / generate legs")
     args = ap.parse_args()

@@ -474,7 +474,8 @@ def test_gemv_bf16_baseline_shapes_vs_c_oracle(K, nbits, fin, fout):
 
 # ---- Kx8 dot-product-LUT GEMV (batch 1) -------------------------------------------------------------------------
 @pytest.mark.parametrize("K", [1, 2, 4, 8])
-@pytest.mark.parametrize("fin,fout", [(4096, 4096), (4096, 11008), (11008, 4096), (1032, 77), (264, 33)])
+@pytest.mark.parametrize("fin,fout", [(4096, 4096), (4096, 11008), (11008, 4096), (1032, 77), (264, 33), (1040, 77),
+                                      (2048, 300), (16, 5)])
 def test_lut_gemv_kx8(K, fin, fout):
     """BASELINE configs[2] shapes (Llama-2-7B: q/k/v/o, gate/up, down) plus ragged sizes (in_groups not a multiple of the
     slab), all rows against the C oracle."""

@@ -58,6 +58,37 @@ def main():
         xi = torch.randn((1, 14336), dtype=torch.float16, device=DEV)
         for _ in range(reps):
             qkv(x); o(x); gu(x); down(xi)
+    elif case.startswith("shards_70b_n"):  # the 4 fused GEMV+exchange launches of one Llama-3-70B layer on 1/N-size shards
+        import torch.distributed as dist
+
+        import aqlm_b200
+        from aqlm_b200.grouped import ShardedQuantizedLinearGroup
+        from aqlm_b200.peer import PeerComm
+        from aqlm_b200.sharded import ShardedQuantizedLinear
+
+        n = int(case[len("shards_70b_n"):])
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+        comm = PeerComm(max_elems=4 * 28672)  # a one-rank communicator: the kernel pushes to itself, same DRAM traffic
+
+        def lin(fin, fout):
+            m = ShardedQuantizedLinear(fin // n, fout, 8, 1, 1, 16, bias=False, rank=0, world_size=1, device=DEV,
+                                       dtype=torch.float16, peer_comm=comm)
+            m.world_size = 2  # take the exchange path (the communicator itself has one rank)
+            m.in_begin, m.in_end = 0, fin // n
+            m.codes.data, m.codebooks.data, m.scales.data = weights(fin // n, fout, 1, 16, torch.float16)
+            return m
+        qkv = ShardedQuantizedLinearGroup([lin(8192, 8192), lin(8192, 1024), lin(8192, 1024)])
+        o = lin(8192, 8192)
+        gu = ShardedQuantizedLinearGroup([lin(8192, 28672), lin(8192, 28672)])
+        down = lin(28672, 8192)
+        x = torch.randn((1, 8192 // n), dtype=torch.float16, device=DEV)
+        xi = torch.randn((1, 28672 // n), dtype=torch.float16, device=DEV)
+        for _ in range(reps):
+            qkv(x); o(x); gu(x); down(xi)
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        return
     else:
         raise SystemExit(f"unknown case {case}")
     torch.cuda.synchronize()
