@@ -12,7 +12,8 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libaqlm_b200.so")
+# AQLM_B200_LIB overrides the library file (used by tools/ to compare two builds side by side)
+LIB_PATH = os.environ.get("AQLM_B200_LIB") or os.path.join(CSRC, "libaqlm_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "aqlm_b200.h")
 SOURCES = ["capi.cu"]
 NVCC_FLAGS = [

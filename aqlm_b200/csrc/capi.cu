@@ -58,7 +58,7 @@ static int env_int(const char* name, int dflt) {
 struct Tunables {
   int pdl, gemv_ctas_per_sm, gemv_threads, gather_mode, gemv_v2, force_generic;
   int disable_lut, lut_ctas_per_sm, lut_debug, lut_cluster, lut_batch_loop;
-  int disable_tcgen05, gemm_stages, gemm_ksplit, gemm_cluster, gemm_debug, gemm_gather_mode, gemm_v2, gemm_tile_m, gemm_atmem;
+  int disable_tcgen05, gemm_stages, gemm_ksplit, gemm_cluster, gemm_debug, gemm_gather_mode, gemm_v2, gemm_tile_m, gemm_atmem, gemm_a_stages, gemm_groups;
   void load() {
     pdl = env_int("AQLM_B200_PDL", 1);
     gemv_ctas_per_sm = env_int("AQLM_B200_GEMV_CTAS_PER_SM", 1);
@@ -79,6 +79,8 @@ struct Tunables {
     gemm_gather_mode = env_int("AQLM_B200_GEMM_GATHER_MODE", -1);  // -1: per scheme (1x16: ld.global.cg, no L1 allocation of the 1 MiB codebook's lines; 256-entry codebooks: L1-resident)
     gemm_v2 = env_int("AQLM_B200_GEMM_V2", -1);                   // -1: per-scheme default
     gemm_tile_m = env_int("AQLM_B200_GEMM_TILE_M", 0);            // 0: chosen by the plan
+    gemm_a_stages = env_int("AQLM_B200_GEMM_A_STAGES", 0);        // ATMEM: A stages in tensor memory (0: 6)
+    gemm_groups = env_int("AQLM_B200_GEMM_GROUPS", 0);            // ATMEM: producer groups of 4 warps (0: 3, max 4)
     gemm_atmem = env_int("AQLM_B200_GEMM_ATMEM", -1);             // A operand in tensor memory; -1: per-scheme default
   }
 };
@@ -540,6 +542,7 @@ struct GemmPlan {
   int tile_m = kGemmBlockM;  // output rows per CTA tile
   bool v2 = false;           // producer mapping: one 4-warp group per stage, thread <-> row
   bool atmem = false;        // A operand written to tensor memory (needs v2)
+  int a_stages = 0, groups = 0;  // ATMEM: A stages in TMEM (decoupled from the X stages) / V2: producer groups
   size_t counters_bytes = 0, partials_bytes = 0;
 };
 
@@ -565,7 +568,8 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   }
   // producer mapping V2 (one 4-warp group per stage) measured: 1x16 496 vs 505 TFLOP/s (V1), 2x8 134 vs 394, 8x8 196 vs 119
   // -> V2 for schemes with many codebooks; A-in-TMEM builds on V2 (profiles/r01/gemm_experiments.md, profiles/r02/)
-  g.atmem = (tun().gemm_atmem < 0 ? (K == 1) : tun().gemm_atmem != 0) && !(tun().gemm_debug & 1);
+  // A in tensor memory: measured 1x16 61.7 -> 55.1 us, 2x8 69.3 -> 49.2 us (4096->14336/11008, bs=256); 8x8 no gain
+  g.atmem = (tun().gemm_atmem < 0 ? (K <= 2) : tun().gemm_atmem != 0) && !(tun().gemm_debug & 1);
   g.v2 = g.atmem || ((tun().gemm_v2 < 0 ? (K >= 4 ? 1 : 0) : tun().gemm_v2) != 0 && !(tun().gemm_debug & 1));
   const size_t budget = (size_t)di->max_smem_optin;
   // At most 3 stages: shared memory taken here is L1 taken from the codebook gathers (outstanding misses need L1
@@ -575,8 +579,20 @@ static GemmPlan gemm_plan(const aqlm_b200_weight_t* w, int64_t batch, const Devi
   if (gemm_smem_layout(S, g.n_tile, g.atmem).total > budget) return g;
   const int forced_s = tun().gemm_stages;
   if (forced_s >= 2 && forced_s <= S) S = forced_s;
-  if (forced_s == 4 && g.v2 && gemm_smem_layout(4, g.n_tile, g.atmem).total <= budget) S = 4;  // experiment: 4 producer groups
+  if (forced_s == 4 && g.v2 && gemm_smem_layout(4, g.n_tile, g.atmem).total <= budget) S = 4;  // experiment: 4 X stages
   g.stages = S;
+  g.groups = S;
+  g.a_stages = S;
+  if (g.atmem) {
+    // tensor memory: accumulator columns [0, n_tile), then 32 columns per A stage; 512 columns in all
+    const int room = (512 - ((g.n_tile + 31) & ~31)) / 32;
+    int sa = tun().gemm_a_stages > 0 ? tun().gemm_a_stages : 6;
+    if (sa > room) sa = room;
+    if (sa > 8) sa = 8;
+    if (sa < 2) sa = 2;
+    g.a_stages = sa;
+    g.groups = tun().gemm_groups > 0 ? (tun().gemm_groups > 4 ? 4 : tun().gemm_groups) : 3;
+  }
   // ---- tile height and split-K: a small cost model over (tile_m, ksplit), in SM clocks ----
   //   per k-block of one CTA: max(gathers, tensor pipe, shared-memory traffic) + a fixed synchronisation cost;
   //   per CTA: its k-blocks + a fixed cost (launch ramp, TMEM alloc, pipeline fill, epilogue: ~5 us measured);
@@ -677,6 +693,8 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   p.ksplit = g.ksplit;
   p.n_tile = g.n_tile;
   p.stages = g.stages;
+  p.a_stages = g.a_stages;
+  p.groups = g.groups;
   p.tile_m = g.tile_m;
   p.cluster = g.cluster;
   p.debug = tun().gemm_debug;
@@ -695,13 +713,15 @@ static int launch_gemm(const aqlm_b200_weight_t* w, const void* input, void* out
   cfg.blockDim = dim3(v2 ? kGemmThreadsV2 : kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = g.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tx, tc, p));
   count_launch();
   return AQLM_B200_OK;
@@ -838,9 +858,18 @@ static int launch_gemm_t(const aqlm_b200_weight_t* w, const void* grad_output, v
   auto kernel = gemm_dequant_t_kernel<T, K, CB>;
   static SmemMarks marks;
   if (int rc = ensure_smem(kernel, smem, marks, di)) return rc;
-  kernel<<<dim3(g.m_tiles, g.ksplit, g.n_tiles), kGemmTThreads, smem, st>>>(tg, tc, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.m_tiles, g.ksplit, g.n_tiles);
+  cfg.blockDim = dim3(kGemmTThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tg, tc, p));
   count_launch();
-  AQLM_CUDA_CHECK(cudaGetLastError());
   return AQLM_B200_OK;
 }
 

@@ -46,6 +46,8 @@ struct GemmParams {
   int n_tile;           // N of the MMA (multiple of 16, <= 256)
   int stages;
   int cluster;          // CTAs per cluster along M that share (multicast) the X tiles
+  int a_stages;         // ATMEM: number of 32-column A stages in tensor memory (decoupled from the X stages in smem)
+  int groups;           // V2: producer groups of 4 warps (coupled form: = stages)
   int tile_m;           // output rows per CTA tile (<= 128): ragged tile heights balance the grid (e.g. 97 rows -> 148 tiles of 14336)
   int gather_mode;      // 0: ld.global.nc (L1 allocate), 1: ld.global.cg, 3: nc.L1::no_allocate
   int debug;            // bit0: read codes from global instead of the TMA code tile; bit1: no producer run-ahead
@@ -89,6 +91,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
+}
+// one lane of a converged warp (uniform control flow around it lets ptxas keep descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -146,7 +154,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
 
 // shared-memory carve-up (all offsets from a 1024-byte aligned base)
 struct GemmSmem {
-  uint32_t a, b, codes, full, empty, cfull, cempty, tfull, tmem_slot, flag;
+  uint32_t a, b, codes, full, empty, afull, aempty, cfull, cempty, tfull, tmem_slot, flag;
   size_t total;
 };
 __host__ __device__ inline GemmSmem gemm_smem_layout(int stages, int n_tile, bool a_in_tmem = false) {
@@ -158,6 +166,8 @@ __host__ __device__ inline GemmSmem gemm_smem_layout(int stages, int n_tile, boo
   L.codes = (uint32_t)off; off += (size_t)kCodeTileStages * kGemmBlockM * kCodeTileBytes;
   L.full = (uint32_t)off; off += 8 * 8;
   L.empty = (uint32_t)off; off += 8 * 8;
+  L.afull = (uint32_t)off; off += 8 * 8;
+  L.aempty = (uint32_t)off; off += 8 * 8;
   L.cfull = (uint32_t)off; off += 8 * kCodeTileStages;
   L.cempty = (uint32_t)off; off += 8 * kCodeTileStages;
   L.tfull = (uint32_t)off; off += 8;
@@ -196,6 +206,10 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, split = blockIdx.y, n_blk = blockIdx.z;
   const int m0 = m_tile * TM, n0 = n_blk * N;
+  // PDL: the next kernel of the stream may be dispatched as soon as SM resources free up (no launch gap).  Everything this
+  // kernel does before griddep_wait() touches WEIGHTS only (code tiles, codebook gathers); the X tiles are read and y /
+  // the workspace written after it.
+  griddep_launch_dependents();
   // k-block range of this split (balanced, contiguous)
   const int kb0 = (int)(((long long)p.total_kblocks * split) / p.ksplit);
   const int kb1 = (int)(((long long)p.total_kblocks * (split + 1)) / p.ksplit);
@@ -208,17 +222,30 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   auto empty_bar = [&](int s) { return base + L.empty + 8 * s; };
   auto cfull_bar = [&](int s) { return base + L.cfull + 8 * s; };
   auto cempty_bar = [&](int s) { return base + L.cempty + 8 * s; };
+  // ATMEM: the A stages (tensor memory) have their own full/empty barriers, decoupled from the X stages (shared memory):
+  // the dequant producers run up to SA k-blocks ahead of the MMA no matter how late an X tile lands
+  auto afull_bar = [&](int s) { return base + L.afull + 8 * s; };
+  auto aempty_bar = [&](int s) { return base + L.aempty + 8 * s; };
+  const int SA = ATMEM ? p.a_stages : S;
+  const int G = V2 ? p.groups : 0;  // producer groups
   const uint32_t tfull_bar = base + L.tfull;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L.tmem_slot);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), (V2 ? 4 : kGemmProducerWarps) + 1);  // producer warps of the stage + the TMA thread (expect_tx)
+      // X stage: the TMA thread's expect_tx arrival (+ the stage's producer warps when A shares the stage)
+      mbar_init(full_bar(s), ATMEM ? 1 : (V2 ? 4 : kGemmProducerWarps) + 1);
       mbar_init(empty_bar(s), C);                      // tcgen05.commit of every CTA in the cluster
+    }
+    if constexpr (ATMEM) {
+      for (int s = 0; s < SA; ++s) {
+        mbar_init(afull_bar(s), 4);   // the 4 warps of the group that owns the k-block
+        mbar_init(aempty_bar(s), 1);  // tcgen05.commit
+      }
     }
     for (int s = 0; s < kCodeTileStages; ++s) {
       mbar_init(cfull_bar(s), 1);
-      mbar_init(cempty_bar(s), V2 ? 4 * S : kGemmProducerWarps);
+      mbar_init(cempty_bar(s), V2 ? 4 * G : kGemmProducerWarps);
     }
     mbar_init(tfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -226,7 +253,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   // accumulator: columns [0, N); with ATMEM the A stages follow at a 32-column aligned offset, 32 columns per stage
   const uint32_t a_col0 = (uint32_t)((N + 31) & ~31);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (ATMEM ? a_col0 + 32u * (uint32_t)S : (uint32_t)N)) tmem_cols <<= 1;
+  while (tmem_cols < (ATMEM ? a_col0 + 32u * (uint32_t)p.a_stages : (uint32_t)N)) tmem_cols <<= 1;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L.tmem_slot), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -238,64 +265,87 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (nkb > 0) {
-    if (warp == 0 && lane == 0) {
-      // ===== TMA producer: code tiles (one per KB_PER_CTILE k-blocks) and one X tile per k-block =====
+    if (warp == 0) {
+      // ===== TMA producer (whole warp, one elected lane issues): code tiles (one per KB_PER_CTILE k-blocks) and one X
+      //       tile per k-block =====
       int ct_loaded = ct0;
       auto load_ctile = [&](int ct) {
         const int cs = (ct - ct0) % kCodeTileStages;
         const int it = (ct - ct0) / kCodeTileStages;
         if (it > 0) mbar_wait(cempty_bar(cs), (it - 1) & 1);  // every producer warp released the previous tenant
-        mbar_expect_tx(cfull_bar(cs), (uint32_t)TM * kCodeTileBytes);  // the TMA box is tile_m rows tall
-        tma_load_2d(base + L.codes + cs * kGemmBlockM * kCodeTileBytes, &tmap_codes, ct * kCodeTileBytes, m0, cfull_bar(cs));
+        if (elect_one()) {
+          mbar_expect_tx(cfull_bar(cs), (uint32_t)TM * kCodeTileBytes);  // the TMA box is tile_m rows tall
+          tma_load_2d(base + L.codes + cs * kGemmBlockM * kCodeTileBytes, &tmap_codes, ct * kCodeTileBytes, m0, cfull_bar(cs));
+        }
+        __syncwarp();
       };
       load_ctile(ct_loaded++);
+      griddep_wait();  // X is produced by the previous kernel
+      int s = 0, it = 0;  // X stage and its use count (no runtime division in this loop)
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % S, it = i / S;
         if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
-        if (p.debug & 4) {  // experiment: no X traffic (B tile keeps whatever it holds)
-          mbar_arrive(full_bar(s));
-        } else if (C == 1) {
-          mbar_expect_tx(full_bar(s), (uint32_t)N * 128);
-          tma_load_2d(base + L.b + s * N * 128, &tmap_x, (kb0 + i) * kGemmBlockK, n0, full_bar(s));
-        } else {
-          mbar_expect_tx(full_bar(s), (uint32_t)N * 128);  // all C slices land here
-          // this CTA fetches rows [crank*N/C, (crank+1)*N/C) of the X tile and multicasts them to the whole cluster;
-          // empty_bar(s) (count C) guarantees every CTA of the cluster has released stage s
-          const int rows = N / C;
-          tma_load_2d_mc(base + L.b + s * N * 128 + crank * rows * 128, &tmap_x, (kb0 + i) * kGemmBlockK, n0 + crank * rows,
-                         full_bar(s), cmask);
+        if (elect_one()) {
+          if (p.debug & 4) {  // experiment: no X traffic (B tile keeps whatever it holds)
+            mbar_arrive(full_bar(s));
+          } else if (C == 1) {
+            mbar_expect_tx(full_bar(s), (uint32_t)N * 128);
+            tma_load_2d(base + L.b + s * N * 128, &tmap_x, (kb0 + i) * kGemmBlockK, n0, full_bar(s));
+          } else {
+            mbar_expect_tx(full_bar(s), (uint32_t)N * 128);  // all C slices land here
+            // this CTA fetches rows [crank*N/C, (crank+1)*N/C) of the X tile and multicasts them to the whole cluster;
+            // empty_bar(s) (count C) guarantees every CTA of the cluster has released stage s
+            const int rows = N / C;
+            tma_load_2d_mc(base + L.b + s * N * 128 + crank * rows * 128, &tmap_x, (kb0 + i) * kGemmBlockK, n0 + crank * rows,
+                           full_bar(s), cmask);
+          }
         }
+        __syncwarp();
         // prefetch the NEXT code tile while the producers work on the current one
         const int ct_cur = (kb0 + i) / KB_PER_CTILE;
         if (ct_loaded < ct1 && ct_loaded <= ct_cur + 1) load_ctile(ct_loaded++);
+        if (++s == S) { s = 0; ++it; }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ===== MMA issuer =====
+    } else if (warp == 1) {
+      // ===== MMA issuer: the WHOLE warp runs the loop (uniform barrier waits, incremental stage counters), one elected
+      //       lane issues.  A lane-0-only loop compiled to ~150 dependent scalar instructions per k-block (runtime
+      //       modulo, R2UR moves, an election loop around every UTCHMMA): ~1000 clk per k-block against 512 clk of MMA --
+      //       with gathers AND X loads switched off the kernel still took 44.6 us (profiles/r02/probe_gemm_e1.jsonl). =====
       const uint32_t idesc = umma_idesc(sizeof(T) == 2 && DT<T>::is_bf16 ? 1 : 0, N);
+      int s = 0, sa = 0;
+      uint32_t ph_b = 0, ph_a = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % S, it = i / S;
-        mbar_wait(full_bar(s), it & 1);
+        mbar_wait(full_bar(s), ph_b);
+        if constexpr (ATMEM) mbar_wait(afull_bar(sa), ph_a);
         tc_fence_after();
-        const uint32_t a_addr = base + L.a + s * kGemmBlockM * 128;
-        const uint32_t b_addr = base + L.b + s * N * 128;
+        if (elect_one()) {
+          const uint32_t a_addr = base + L.a + s * kGemmBlockM * 128;
+          const uint32_t b_addr = base + L.b + s * N * 128;
+          const uint64_t bdesc = umma_desc_k128(b_addr);
 #pragma unroll
-        for (int k = 0; k < kGemmBlockK / 16; ++k) {
-          if constexpr (ATMEM)
-            umma_f16_ts(tmem_base, tmem_base + a_col0 + (uint32_t)(s * 32 + k * 8), umma_desc_k128(b_addr + k * 32), idesc, (i | k) ? 1u : 0u);
-          else
-            umma_f16(tmem_base, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc, (i | k) ? 1u : 0u);
+          for (int k = 0; k < kGemmBlockK / 16; ++k) {
+            // advancing 16 K-elements = 32 bytes = +2 in the descriptor's (address >> 4) field
+            if constexpr (ATMEM)
+              umma_f16_ts(tmem_base, tmem_base + a_col0 + (uint32_t)(sa * 32 + k * 8), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+            else
+              umma_f16(tmem_base, umma_desc_k128(a_addr) + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+          }
+          // frees this smem stage (in every CTA of the cluster) when the MMAs above have read it
+          if (C == 1) umma_commit(empty_bar(s));
+          else umma_commit_mc(empty_bar(s), cmask);
+          if constexpr (ATMEM) umma_commit(aempty_bar(sa));  // and the A stage (this CTA's tensor memory only)
         }
-        // frees this smem stage (in every CTA of the cluster) when the MMAs above have read it
-        if (C == 1) umma_commit(empty_bar(s));
-        else umma_commit_mc(empty_bar(s), cmask);
+        __syncwarp();
+        if (++s == S) { s = 0; ph_b ^= 1u; }
+        if (++sa == SA) { sa = 0; ph_a ^= 1u; }
       }
-      umma_commit(tfull_bar);  // accumulator complete
+      if (elect_one()) umma_commit(tfull_bar);  // accumulator complete
+      __syncwarp();
     } else if (warp >= 4) {
       if constexpr (V2) {
         // ===== V2 dequant producers: group g (4 warps, thread <-> row) owns stage g and every S-th k-block =====
         const int pw = warp - 4;
         const int g = pw >> 2;
-        if (g < S) {
+        if (g < G) {
           const int row = (pw & 3) * 32 + lane;
           const bool active = row < TM;  // rows past the (ragged) tile height: no gathers, nothing to write
           const uint4* gcb = reinterpret_cast<const uint4*>(p.codebooks);
@@ -343,7 +393,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           };
           auto gather_all = [&](const uint32_t (&cw)[CWN], uint4 (&wv)[8][INREG ? K : 1]) {
             if constexpr (INREG) {
-              if (active) {
+              if (active && !(p.debug & 8)) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
 #pragma unroll
@@ -360,9 +410,15 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
               }
             }
           };
+          // this group's k-blocks are g, g+G, g+2G, ...: their A stage and use count advance incrementally
+          const int NSTG = ATMEM ? SA : S;
+          int st_next = g % NSTG, it_next = g / NSTG;
           auto commit = [&](int i, const uint32_t (&cw)[CWN], uint4 (&wv)[8][INREG ? K : 1]) {
-            const int s = i % S, it = i / S;
-            if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
+            (void)i;
+            const int s = st_next, it = it_next;
+            st_next += G;
+            while (st_next >= NSTG) { st_next -= NSTG; ++it_next; }
+            if (it > 0) mbar_wait(ATMEM ? aempty_bar(s) : empty_bar(s), (it - 1) & 1);
             uint8_t* arow = gbase + L.a + s * kGemmBlockM * 128 + row * 128;
             uint32_t areg[32];  // ATMEM: the row's 64 halves in K order (= the TMEM column order)
             if constexpr (ATMEM) tc_fence_after();  // the stage's previous reader (MMA) is ordered before these writes
@@ -406,25 +462,25 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
               fence_proxy_async();
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));
+            if (lane == 0) mbar_arrive(ATMEM ? afull_bar(s) : full_bar(s));
           };
           if constexpr (DB) {
             uint32_t ca[CWN], cb[CWN];
             uint4 wa[8][K], wb[8][K];
             int i = g;
             if (i < nkb) { load_cw(i, ca); gather_all(ca, wa); }
-            for (; i < nkb; i += 2 * S) {
-              if (i + S < nkb) { load_cw(i + S, cb); gather_all(cb, wb); }
+            for (; i < nkb; i += 2 * G) {
+              if (i + G < nkb) { load_cw(i + G, cb); gather_all(cb, wb); }
               commit(i, ca, wa);
-              if (i + S < nkb) {
-                if (i + 2 * S < nkb) { load_cw(i + 2 * S, ca); gather_all(ca, wa); }
-                commit(i + S, cb, wb);
+              if (i + G < nkb) {
+                if (i + 2 * G < nkb) { load_cw(i + 2 * G, ca); gather_all(ca, wa); }
+                commit(i + G, cb, wb);
               }
             }
           } else {
             uint32_t ca[CWN];
             uint4 wa[8][INREG ? K : 1];
-            for (int i = g; i < nkb; i += S) {
+            for (int i = g; i < nkb; i += G) {
               load_cw(i, ca);
               gather_all(ca, wa);
               commit(i, ca, wa);
@@ -545,12 +601,16 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
   }
 
-  // ===== epilogue: warps 0-3, thread <-> TMEM lane <-> output row =====
+  // ===== epilogue: ALL warps (a warp may read the TMEM lanes 32*(warp%4)..+31, so the producer warps -- idle by now --
+  //       take column chunks too: 5 warps per lane quadrant instead of 1), thread <-> TMEM lane <-> output row =====
   const size_t tile_id = (size_t)m_tile * gridDim.z + n_blk;
   T* y = reinterpret_cast<T*>(p.y);
-  if (warp < 4) {
-    __syncwarp();  // lanes 1-31 of the TMA / MMA warps wait here for their lane 0 (tcgen05.ld is warp-collective)
-    const int row_in_tile = warp * 32 + lane;
+  {
+    __syncwarp();
+    griddep_wait();  // before any global write (y, split-K partials): the previous kernel has completed
+    constexpr int kParts = NTHREADS / 128;
+    const int quad = warp & 3, part = warp >> 2;
+    const int row_in_tile = quad * 32 + lane;
     const int row = m0 + row_in_tile;
     const bool row_ok = row_in_tile < TM && row < p.out_features;
     float sc = 1.f, bi = 0.f;
@@ -563,10 +623,10 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       tc_fence_after();
     }
     float* my_part = p.ws_partials ? p.ws_partials + ((tile_id * p.ksplit + split) * (size_t)N) * kGemmBlockM : nullptr;
-    for (int c0 = 0; c0 < N; c0 += 32) {
+    for (int c0 = part * 32; c0 < N; c0 += kParts * 32) {
       uint32_t r[32];
       if (nkb > 0) {
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
       } else {
 #pragma unroll
         for (int c = 0; c < 32; ++c) r[c] = 0u;
@@ -575,7 +635,7 @@ gemm_dequant_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int n = n0 + c0 + c;
-          if (row_ok && c0 + c < N && n < p.batch) y[(size_t)n * p.out_features + row] = DT<T>::from_float(fmaf(__uint_as_float(r[c]), sc, bi));
+          if (row_ok && c0 + c < N && n < p.batch && !(p.debug & 16)) y[(size_t)n * p.out_features + row] = DT<T>::from_float(fmaf(__uint_as_float(r[c]), sc, bi));
         }
       } else {
 #pragma unroll

@@ -91,6 +91,7 @@ gemm_dequant_t_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
   const int kb1 = (int)(((long long)p.total_kblocks * (split + 1)) / p.ksplit);
   const int nkb = kb1 - kb0;
   const int ct0 = kb0 / KB_PER_CTILE, ct1 = (kb1 + KB_PER_CTILE - 1) / KB_PER_CTILE;
+  griddep_launch_dependents();  // PDL, as in the forward kernel: weights before griddep_wait(), grad_out / outputs after
 
   auto full_bar = [&](int s) { return base + L.full + 8 * s; };
   auto empty_bar = [&](int s) { return base + L.empty + 8 * s; };
@@ -123,41 +124,59 @@ gemm_dequant_t_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (nkb > 0) {
-    if (warp == 0 && lane == 0) {
-      // ===== TMA producer: code tiles (256 out rows x GBT bytes) and one grad_out tile per k-block =====
+    if (warp == 0) {
+      // ===== TMA producer (whole warp, one elected lane issues): code tiles (256 out rows x GBT bytes) and one grad_out
+      //       tile per k-block =====
       int ct_loaded = ct0;
       auto load_ctile = [&](int ct) {
         const int cs = (ct - ct0) % kCodeTileStages, it = (ct - ct0) / kCodeTileStages;
         if (it > 0) mbar_wait(cempty_bar(cs), (it - 1) & 1);
-        mbar_expect_tx(cfull_bar(cs), kGemmTCtileRows * GBT);
-        tma_load_2d(base + L.codes + cs * kGemmTCtileRows * GBT, &tmap_codes, m_tile * GBT, ct * kGemmTCtileRows, cfull_bar(cs));
+        if (elect_one()) {
+          mbar_expect_tx(cfull_bar(cs), kGemmTCtileRows * GBT);
+          tma_load_2d(base + L.codes + cs * kGemmTCtileRows * GBT, &tmap_codes, m_tile * GBT, ct * kGemmTCtileRows, cfull_bar(cs));
+        }
+        __syncwarp();
       };
       load_ctile(ct_loaded++);
+      griddep_wait();  // grad_out is produced by the previous kernel
+      int s = 0, it = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % S, it = i / S;
         if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
-        mbar_expect_tx(full_bar(s), (uint32_t)N * 128);
-        tma_load_2d(base + L.b + s * N * 128, &tmap_g, (kb0 + i) * kGemmBlockK, n0, full_bar(s));
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), (uint32_t)N * 128);
+          tma_load_2d(base + L.b + s * N * 128, &tmap_g, (kb0 + i) * kGemmBlockK, n0, full_bar(s));
+        }
+        __syncwarp();
         const int ct_cur = (kb0 + i) / KB_PER_CTILE;
         if (ct_loaded < ct1 && ct_loaded <= ct_cur + 1) load_ctile(ct_loaded++);
+        if (++s == S) { s = 0; ++it; }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ===== MMA issuer: A MN-major (a_major bit 15), B K-major =====
+    } else if (warp == 1) {
+      // ===== MMA issuer (whole warp, one elected lane issues; see gemm_tcgen05.cuh): A MN-major (a_major bit 15), B K-major =====
       const uint32_t idesc = umma_idesc(DT<T>::is_bf16 ? 1 : 0, N) | (1u << 15);
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % S, it = i / S;
-        mbar_wait(full_bar(s), it & 1);
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t a_addr = base + L.a + s * kGemmBlockM * 128;
-        const uint32_t b_addr = base + L.b + s * N * 128;
+        if (elect_one()) {
+          const uint32_t a_addr = base + L.a + s * kGemmBlockM * 128;
+          const uint32_t b_addr = base + L.b + s * N * 128;
+          const uint64_t adesc = umma_desc_mn128(a_addr, 1024, 2048);
+          const uint64_t bdesc = umma_desc_k128(b_addr);
 #pragma unroll
-        for (int k = 0; k < kGemmBlockK / 16; ++k) {
-          // one MMA covers 16 out rows = 2 K-atoms of the stage: atoms are laid out [k_atom (8)][m_atom (2)][1024 B]
-          umma_f16(tmem_base, umma_desc_mn128(a_addr + k * 4096, 1024, 2048), umma_desc_k128(b_addr + k * 32), idesc, (i | k) ? 1u : 0u);
+          for (int k = 0; k < kGemmBlockK / 16; ++k) {
+            // one MMA covers 16 out rows = 2 K-atoms of the stage: atoms are laid out [k_atom (8)][m_atom (2)][1024 B], so
+            // A advances by 4096 bytes (+256 in the address field), B by 32 bytes (+2)
+            umma_f16(tmem_base, adesc + (uint64_t)(256 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
         }
-        umma_commit(empty_bar(s));
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
-      umma_commit(tfull_bar);
+      if (elect_one()) umma_commit(tfull_bar);
+      __syncwarp();
     } else if (warp >= 4) {
       // ===== dequant producers: 512 threads, thread -> (out row kk of the k-block, 2 adjacent in-groups) =====
       const int pt = threadIdx.x - 128;
@@ -244,12 +263,15 @@ gemm_dequant_t_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
     }
   }
 
-  // ===== epilogue: warps 0-3, thread <-> TMEM lane <-> in-feature =====
+  // ===== epilogue: all warps (5 per TMEM lane quadrant), thread <-> TMEM lane <-> in-feature =====
   const size_t tile_id = (size_t)m_tile * gridDim.z + n_blk;
   T* y = reinterpret_cast<T*>(p.y);
-  if (warp < 4) {
+  {
     __syncwarp();
-    const int row_in_tile = warp * 32 + lane;
+    griddep_wait();  // before any global write
+    constexpr int kParts = kGemmTThreads / 128;
+    const int quad = warp & 3, part = warp >> 2;
+    const int row_in_tile = quad * 32 + lane;
     const int col = m0 + row_in_tile;  // in-feature index
     const bool col_ok = col < p.in_features;
     if (nkb > 0) {
@@ -257,10 +279,10 @@ gemm_dequant_t_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
       tc_fence_after();
     }
     float* my_part = p.ws_partials ? p.ws_partials + ((tile_id * p.ksplit + split) * (size_t)N) * kGemmBlockM : nullptr;
-    for (int c0 = 0; c0 < N; c0 += 32) {
+    for (int c0 = part * 32; c0 < N; c0 += kParts * 32) {
       uint32_t r[32];
       if (nkb > 0) {
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
       } else {
 #pragma unroll
         for (int c = 0; c < 32; ++c) r[c] = 0u;

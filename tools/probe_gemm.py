@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 from aqlm_b200 import _cabi  # noqa: E402
 from aqlm_b200.inference_kernels import cuda_kernel  # noqa: E402
 
-KEYS = ["GEMM_ATMEM", "GEMM_TILE_M", "GEMM_KSPLIT", "GEMM_STAGES", "GEMM_V2", "GEMM_GATHER_MODE", "GEMM_DEBUG", "GEMM_CLUSTER"]
+KEYS = ["PDL", "GEMM_A_STAGES", "GEMM_GROUPS", "GEMM_ATMEM", "GEMM_TILE_M", "GEMM_KSPLIT", "GEMM_STAGES", "GEMM_V2", "GEMM_GATHER_MODE", "GEMM_DEBUG", "GEMM_CLUSTER"]
 
 
 def timed(fns, iters=10):
