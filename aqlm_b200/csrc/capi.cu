@@ -57,7 +57,7 @@ static int env_int(const char* name, int dflt) {
 // calls aqlm_b200_reload_tunables() after changing the environment.  Defaults are the shipped configuration.
 struct Tunables {
   int pdl, gemv_ctas_per_sm, gemv_threads, gather_mode, gemv_v2, force_generic;
-  int disable_lut, lut_ctas_per_sm, lut_debug, lut_cluster, lut_batch_loop;
+  int disable_lut, lut_ctas_per_sm, lut_debug, lut_cluster, lut_batch_loop, lut_rb16;
   int disable_tcgen05, gemm_stages, gemm_ksplit, gemm_cluster, gemm_debug, gemm_gather_mode, gemm_v2, gemm_tile_m, gemm_atmem, gemm_a_stages, gemm_groups;
   void load() {
     pdl = env_int("AQLM_B200_PDL", 1);
@@ -70,6 +70,7 @@ struct Tunables {
     lut_ctas_per_sm = env_int("AQLM_B200_LUT_CTAS_PER_SM", 2);  // 128 regs x 256 threads: registers allow 2
     lut_debug = env_int("AQLM_B200_LUT_DEBUG", 0);
     lut_batch_loop = env_int("AQLM_B200_LUT_BATCH_LOOP", 1);  // batch 2-3 on 256-entry codebooks: one LUT launch per row
+    lut_rb16 = env_int("AQLM_B200_LUT_RB16", 0);  // cluster kernel: 16-row warp batches on 768 threads (experiment)
     lut_cluster = env_int("AQLM_B200_LUT_CLUSTER", 1);  // K <= 2, in <= 4096: slab CTAs form a cluster, DSMEM reduction
     disable_tcgen05 = env_int("AQLM_B200_DISABLE_TCGEN05", 0);
     gemm_stages = env_int("AQLM_B200_GEMM_STAGES", 0);
@@ -197,7 +198,7 @@ static int launch_1x16_peer(GemvParams p, const GemvPeer& pc, const DeviceInfo* 
   p.row_block = rb;
   const int chunks = p.in_groups / 8;
   const int slices = (chunks + kSliceChunks - 1) / kSliceChunks;
-  const size_t smem = (size_t)BT * p.in_features * 2 + (size_t)rb * slices * BT * 4 + (size_t)rb * BT * 4;
+  const size_t smem = (size_t)BT * p.in_features * 2 + (size_t)rb * slices * BT * 4;
   if (smem > (size_t)di->max_smem_optin - 1024)
     return fail(AQLM_B200_ERR_UNSUPPORTED, "fused exchange: activation tile + partials do not fit in shared memory");
   auto kernel = gemv_1x16_kernel<T, BT, 0, kGemv1x16Threads, true>;
@@ -425,13 +426,13 @@ static int lut_typed(const aqlm_b200_weight_t* w, const void* input, void* outpu
 }
 
 // ---- Kx8 LUT GEMV, cluster / DSMEM variant (K <= 2, at most 8 slabs of 64 groups): host side ---------------
-template <typename T, int K>
+template <typename T, int K, int RB, int THREADS>
 static int launch_lut_cluster(const aqlm_b200_weight_t* w, const void* input, void* output, uint32_t flags,
                               const DeviceInfo* di, cudaStream_t st, bool* taken) {
   *taken = false;
   const int in_groups = (int)(w->in_features / 8);
   const int n_slabs = (in_groups + kLutCJ - 1) / kLutCJ;
-  auto kernel = gemv_lut_cluster_kernel<T, K>;
+  auto kernel = gemv_lut_cluster_kernel<T, K, RB, THREADS>;
   const size_t lut_bytes = (size_t)K * 256 * kLutCJ * 4;
   // how many clusters of n_slabs CTAs can be resident at once: the grid must be ONE wave (a second wave doubles the time)
   static std::atomic<int> max_clusters[kMaxDevices][9];
@@ -445,7 +446,7 @@ static int launch_lut_cluster(const aqlm_b200_weight_t* w, const void* input, vo
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.blockDim = dim3(kLutCThreads);
+  cfg.blockDim = dim3(THREADS);
   cfg.stream = st;
   static SmemMarks marks;
   if (mc == 0) {
@@ -500,11 +501,14 @@ static int try_lut_cluster(const aqlm_b200_weight_t* w, const void* input, void*
   if (!tun().lut_cluster || tun().disable_lut || tun().lut_debug) return AQLM_B200_OK;
   if ((in_groups & 1) || in_groups > 8 * kLutCJ) return AQLM_B200_OK;
   if ((reinterpret_cast<uintptr_t>(w->codes) & 3) || (reinterpret_cast<uintptr_t>(input) & 3)) return AQLM_B200_OK;
-  if (w->dtype == AQLM_B200_F16)
-    return K == 1 ? launch_lut_cluster<__half, 1>(w, input, output, flags, di, st, taken)
-                  : launch_lut_cluster<__half, 2>(w, input, output, flags, di, st, taken);
-  return K == 1 ? launch_lut_cluster<__nv_bfloat16, 1>(w, input, output, flags, di, st, taken)
-                : launch_lut_cluster<__nv_bfloat16, 2>(w, input, output, flags, di, st, taken);
+#define AQLM_LUTC(T)                                                                                              \
+  (tun().lut_rb16 ? (K == 1 ? launch_lut_cluster<T, 1, 16, 768>(w, input, output, flags, di, st, taken)             \
+                            : launch_lut_cluster<T, 2, 16, 768>(w, input, output, flags, di, st, taken))            \
+                  : (K == 1 ? launch_lut_cluster<T, 1, 32, kLutCThreads>(w, input, output, flags, di, st, taken)    \
+                            : launch_lut_cluster<T, 2, 32, kLutCThreads>(w, input, output, flags, di, st, taken)))
+  if (w->dtype == AQLM_B200_F16) return AQLM_LUTC(__half);
+  return AQLM_LUTC(__nv_bfloat16);
+#undef AQLM_LUTC
 }
 
 // ---- fused dequant + tcgen05 GEMM: host side ------------------------------------------------------
@@ -1151,7 +1155,9 @@ struct aqlm_b200_comm {
 
 size_t aqlm_b200_comm_shared_bytes(int world, int64_t max_elems) {
   if (world < 1 || world > kPeerMaxWorld || max_elems <= 0) return 0;
-  return (size_t)kPeerFlagBytes + (size_t)2 * world * (size_t)max_elems * sizeof(float);
+  // flags + [set][src][max_elems] fp32 slots (stand-alone exchange kernel) + [set][src][max_elems] tagged 64-bit words
+  // (exchange fused into the GEMV)
+  return (size_t)kPeerFlagBytes + (size_t)2 * world * (size_t)max_elems * (sizeof(float) + sizeof(unsigned long long));
 }
 
 int aqlm_b200_shared_alloc(size_t bytes, void** ptr, void* handle64) {
@@ -1287,8 +1293,7 @@ int aqlm_b200_matmat_allreduce(aqlm_b200_comm* c, const aqlm_b200_weight_t* w, c
   pc.max_elems = c->max_elems;
   pc.rank = c->rank;
   pc.world = c->world;
-  pc.flag_stride = kPeerFlagStride;
-  pc.flag_bytes = kPeerFlagBytes;
+  pc.ll_offset = (long long)kPeerFlagBytes + (long long)2 * c->world * c->max_elems * (long long)sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int bt = batch == 1 ? 1 : (batch == 2 ? 2 : (batch <= 4 ? 4 : 8));
 #define AQLM_PEER(T)                                                                                    \

@@ -222,23 +222,43 @@ gemm_dequant_t_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
           if (lane == 0) mbar_arrive(cempty_bar(cs));
         }
       };
+      int st_next = 0, it_next = 0;  // commit() runs for k-blocks 0, 1, 2, ... in order: stage / use count without division
       auto commit = [&](int i, uint4 (&wv)[2][K], float sc) {
-        const int s = i % S, it = i / S;
+        (void)i;
+        const int s = st_next, it = it_next;
+        if (++st_next == S) { st_next = 0; ++it_next; }
         if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
         // MN-major SWIZZLE_128B: atom (kk>>3, m_atom) at [(kk>>3)*2 + m_atom]*1024; inside an atom row kk&7 is 128 bytes of
         // 64 consecutive in-features, its 16-byte chunks XOR-swizzled with (kk&7)
         uint8_t* abase = gbase + L.a + s * kGemmBlockM * 128 + (kk >> 3) * 2048 + (kk & 7) * 128;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          float f[8];
-          unpack8<T>(wv[e][0], f);
-#pragma unroll
-          for (int k = 1; k < K; ++k) accum8<T>(wv[e][k], f);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] *= sc;
           uint4 v;
-          v.x = DT<T>::pack2(f[0], f[1]); v.y = DT<T>::pack2(f[2], f[3]);
-          v.z = DT<T>::pack2(f[4], f[5]); v.w = DT<T>::pack2(f[6], f[7]);
+          if constexpr (K == 1) {
+            // one codebook: scale the packed vector with 4 packed multiplies (a 16-bit x 16-bit product is exact in fp32, so
+            // the packed multiply rounds exactly like fp32-multiply-then-round)
+            v = wv[e][0];
+            if constexpr (DT<T>::is_bf16) {
+              const __nv_bfloat162 s2 = __float2bfloat162_rn(sc);
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __hmul2(h[q], s2);
+            } else {
+              const __half2 s2 = __float2half2_rn(sc);
+              __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __hmul2(h[q], s2);
+            }
+          } else {
+            float f[8];
+            unpack8<T>(wv[e][0], f);
+#pragma unroll
+            for (int k = 1; k < K; ++k) accum8<T>(wv[e][k], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] *= sc;
+            v.x = DT<T>::pack2(f[0], f[1]); v.y = DT<T>::pack2(f[2], f[3]);
+            v.z = DT<T>::pack2(f[4], f[5]); v.w = DT<T>::pack2(f[6], f[7]);
+          }
           const int j = gp * 2 + e;  // group 0..15 of the tile = 16-byte chunk j along M
           *reinterpret_cast<uint4*>(abase + (j >> 3) * 1024 + (((j & 7) ^ (kk & 7)) << 4)) = v;
         }

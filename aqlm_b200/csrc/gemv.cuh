@@ -43,8 +43,7 @@ struct GemvPeer {
   unsigned int* tickets;   // local: [2], zero on entry, left zero
   long long max_elems;
   int rank, world;
-  int flag_stride;         // flags per source rank
-  int flag_bytes;          // size of the flag region at the head of each shared buffer
+  long long ll_offset;     // byte offset of the tagged-word slots ([set][src rank][max_elems] u64) in each shared buffer
 };
 
 constexpr int kGemvThreads = 256;  // generic (fallback) kernel
@@ -217,11 +216,10 @@ constexpr int kGemv1x16Threads = 512;
 
 // PEER = true (in_features-sharded multi-GPU path): the kernel's own reduction epilogue performs the ONE exchange of the
 // linear over NVLink peer memory, so a sharded linear is ONE launch and the partials never round-trip through HBM:
-//   every CTA owns a contiguous block of output rows (the same block on every rank); after the fixed-order slice sum it
-//   (A) pushes its fp32 partials into slot [set][my rank] of EVERY rank's buffer with 16-byte P2P stores, (B) publishes
-//   flag[my rank][cta] = step on every rank (st.release.sys, cumulative over the CTA's stores through the barrier),
-//   (C) waits for the W flags of ITS OWN block (ld.acquire.sys) -- CTA c only ever waits for CTA c of the other ranks --
-//   (D) adds the W partial vectors in rank order (deterministic) and applies scale + bias.
+//   every CTA owns a contiguous block of output rows (the same block on every rank); after the fixed-order slice sum each
+//   thread pushes its element as a tagged 64-bit word {fp32, step} to EVERY rank over NVLink and then spins on the W tagged
+//   words of that element in its own buffer, adds them in rank order (deterministic) and applies scale + bias -- no
+//   fence, flag or barrier in between (see the epilogue).  A thread only ever waits for the same element of the other ranks.
 // Two buffer sets alternate by step parity; `step` is read after griddepcontrol.wait (the previous launch, which
 // advances it, has completed).  The grid is one CTA per SM, all co-resident, so the cross-rank wait cannot deadlock.
 template <typename T, int BT, int GM, int THREADS = kGemv1x16Threads, bool PEER = false>
@@ -343,54 +341,42 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) gemv_1x16_kernel(const
       }
     }
   } else {
-    // ---- fused exchange.  sout[b][ri] (fp32) lives behind spart; row_block % 4 == 0 so a block is whole float4s ----
-    float* sout = spart + (size_t)p.row_block * slices * BT;
-    const int RB = p.row_block;
-    for (int i = tid; i < RB * BT; i += THREADS) {
-      const int b = i / RB, ri = i - b * RB;
-      float v = 0.f;
-      if (ri < rows_cta && b < p.batch)
-        for (int sl = 0; sl < slices; ++sl) v += spart[((size_t)ri * slices + sl) * BT + b];
-      sout[i] = v;
-    }
-    __syncthreads();
+    // ---- fused exchange, low-latency form: every value travels as ONE 64-bit word {fp32 bits, step tag} (like NCCL's LL
+    //      protocol), so there is no fence, no flag and no CTA barrier between the push and the reduction: a thread sums
+    //      the slices of its (row, batch) element, stores the tagged word into slot [set][my rank] of EVERY rank (8-byte
+    //      NVLink stores, coalesced across the warp), then spins on the W tagged words of the same element in its OWN buffer
+    //      and adds them in rank order (deterministic).  Two sets alternate by step parity; a tag from two steps ago never
+    //      equals the current step. ----
     const unsigned int s = *pc.step + 1u;  // read after griddep_wait(): the launch that advances it has completed
     const int set = (int)(s & 1u);
-    auto slot = [&](int dst, int src) -> float* {
-      return reinterpret_cast<float*>(pc.peer_base[dst] + pc.flag_bytes) + ((long long)set * pc.world + src) * pc.max_elems;
+    auto slot = [&](int dst, int src) -> unsigned long long* {
+      return reinterpret_cast<unsigned long long*>(pc.peer_base[dst] + pc.ll_offset) + ((long long)set * pc.world + src) * pc.max_elems;
     };
-    const int nv = rows_cta > 0 ? (RB >> 2) : 0;  // float4s per batch row of this CTA's block (the tail block may be padded)
-    // (A) push my block into every rank's slot [set][my rank]
-    for (int i = tid; i < nv * p.batch * pc.world; i += THREADS) {
-      const int r = i / (nv * p.batch);
-      const int j = i - r * (nv * p.batch);
-      const int b = j / nv, q = j - b * nv;
-      const int row = row_first + 4 * q;
-      if (row < p.out_features) {  // out_features % 4 == 0: a float4 never straddles the end
-        const float4 v = *reinterpret_cast<const float4*>(sout + b * RB + 4 * q);
-        *reinterpret_cast<float4*>(slot(r, pc.rank) + (size_t)b * p.out_features + row) = v;
-      }
+    const int nelem = rows_cta * BT;
+    for (int i = tid; i < nelem; i += THREADS) {
+      const int b = i / rows_cta, ri = i - b * rows_cta;
+      if (b >= p.batch) continue;
+      float v = 0.f;
+      for (int sl = 0; sl < slices; ++sl) v += spart[((size_t)ri * slices + sl) * BT + b];
+      const unsigned long long word = ((unsigned long long)s << 32) | (unsigned long long)__float_as_uint(v);
+      const size_t e = (size_t)b * p.out_features + (row_first + ri);
+      for (int r = 0; r < pc.world; ++r)
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot(r, pc.rank) + e), "l"(word) : "memory");
     }
-    // (B) + (C)
-    __syncthreads();
-    if (tid < pc.world) {
-      const int r = tid;
-      unsigned int* theirs = reinterpret_cast<unsigned int*>(pc.peer_base[r]) + pc.rank * pc.flag_stride + blockIdx.x;
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(s) : "memory");
-      const unsigned int* mine = reinterpret_cast<const unsigned int*>(pc.peer_base[pc.rank]) + r * pc.flag_stride + blockIdx.x;
-      unsigned int seen;
-      do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-      } while ((int)(seen - s) < 0);
-    }
-    __syncthreads();
-    // (D) fixed-order sum over source ranks + scale + bias
-    for (int i = tid; i < rows_cta * BT; i += THREADS) {
+    for (int i = tid; i < nelem; i += THREADS) {
       const int b = i / rows_cta, ri = i - b * rows_cta;
       if (b >= p.batch) continue;
       const int row = row_first + ri;
+      const size_t e = (size_t)b * p.out_features + row;
       float acc = 0.f;
-      for (int r = 0; r < pc.world; ++r) acc += __ldcg(slot(pc.rank, r) + (size_t)b * p.out_features + row);
+      for (int r = 0; r < pc.world; ++r) {
+        const unsigned long long* src = slot(pc.rank, r) + e;
+        unsigned long long w;
+        do {
+          asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+        } while ((unsigned int)(w >> 32) != s);
+        acc += __uint_as_float((unsigned int)w);
+      }
       const float sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
       const float bv = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
       reinterpret_cast<T*>(p.y)[(size_t)b * p.out_features + row] = DT<T>::from_float(fmaf(acc, sc, bv));

@@ -297,11 +297,14 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_smem_addr, uint32_t
   return v;
 }
 
-template <typename T, int K>
-__global__ void __launch_bounds__(kLutCThreads, 1) gemv_lut_cluster_kernel(const LutClusterParams p) {
+// RB = rows per warp batch (32: one butterfly of 31 shuffles per 32 rows; 16: 31 shuffles per 16 rows but twice as many,
+// smaller batches to deal to 24 warps -- the row block of a cluster is only ~700 rows = 22 batches of 32).
+template <typename T, int K, int RB = 32, int THREADS = kLutCThreads>
+__global__ void __launch_bounds__(THREADS, 1) gemv_lut_cluster_kernel(const LutClusterParams p) {
   static_assert(K == 1 || K == 2, "cluster LUT kernel: one or two 256-entry codebooks");
+  static_assert(RB == 32 || RB == 16, "rows per warp batch");
   extern __shared__ __align__(16) float lut[];  // [K][256][64], then spart[rows_per_block]
-  constexpr int J = kLutCJ, NT = J / 8, kWarps = kLutCThreads / 32;
+  constexpr int J = kLutCJ, NT = J / 8, kWarps = THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slab = blockIdx.x, rb = blockIdx.y;
   const int j0 = slab * J;
@@ -314,7 +317,6 @@ __global__ void __launch_bounds__(kLutCThreads, 1) gemv_lut_cluster_kernel(const
   using CodeWord = typename std::conditional<K == 2, uint32_t, uint16_t>::type;
   const bool g_ok = j0 + 2 * lane + 1 < p.in_groups;   // (in_groups is even for every shape this kernel accepts)
   const uint8_t* cbase = reinterpret_cast<const uint8_t*>(p.codes) + (size_t)(j0 + 2 * lane) * K;
-  constexpr int RB = 32;
   constexpr int kBatchStride = kWarps * RB;
   auto load_codes = [&](int r0, uint32_t (&cw)[RB]) {
     const uint8_t* src = cbase + (size_t)r0 * row_bytes;
@@ -334,15 +336,15 @@ __global__ void __launch_bounds__(kLutCThreads, 1) gemv_lut_cluster_kernel(const
   int r0 = row_begin + warp * RB;
   load_codes(r0, cwa);
   if (r0 + kBatchStride < row_end) load_codes(r0 + kBatchStride, cwb);
-  constexpr int MT = (K * 16) / kWarps;  // 16-entry tiles per warp
-  static_assert((K * 16) % kWarps == 0, "tiles must divide evenly");
+  constexpr int MT = (K * 16 + kWarps - 1) / kWarps;  // 16-entry tiles per warp (the last pass may be partial)
   const int q = lane >> 2, m = lane & 3;
   uint32_t afrag[MT][2];
   {
     const uint32_t* cb32 = reinterpret_cast<const uint32_t*>(p.codebooks);
 #pragma unroll
     for (int u = 0; u < MT; ++u) {
-      const int e0 = (warp + u * kWarps) * 16;
+      const int tile = warp + u * kWarps;
+      const int e0 = (tile < K * 16 ? tile : 0) * 16;
       afrag[u][0] = __ldg(cb32 + (size_t)(e0 + q) * 4 + m);
       afrag[u][1] = __ldg(cb32 + (size_t)(e0 + q + 8) * 4 + m);
     }
@@ -359,7 +361,9 @@ __global__ void __launch_bounds__(kLutCThreads, 1) gemv_lut_cluster_kernel(const
     }
 #pragma unroll
     for (int u = 0; u < MT; ++u) {
-      const int e0 = (warp + u * kWarps) * 16;
+      const int tile = warp + u * kWarps;
+      if (tile >= K * 16) break;  // (warp-uniform)
+      const int e0 = tile * 16;
       float d[NT][4];
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
@@ -406,8 +410,12 @@ __global__ void __launch_bounds__(kLutCThreads, 1) gemv_lut_cluster_kernel(const
       v[i] = acc;
     }
     if (rbase + 2 * kBatchStride < row_end) load_codes(rbase + 2 * kBatchStride, cw);
+    if constexpr (RB == 16) {  // 16 rows over 32 lanes: fold the two half-warps first, then transpose-reduce over 16 lanes
 #pragma unroll
-    for (int dd = 16, n = RB; dd >= 1; dd >>= 1, n >>= 1) {
+      for (int i = 0; i < RB; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+    }
+#pragma unroll
+    for (int dd = (RB == 32 ? 16 : 8), n = RB; dd >= 1; dd >>= 1, n >>= 1) {
       const bool up = (lane & dd) != 0;
 #pragma unroll
       for (int i = 0; i < n / 2; ++i) {
@@ -416,8 +424,8 @@ __global__ void __launch_bounds__(kLutCThreads, 1) gemv_lut_cluster_kernel(const
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, dd);
       }
     }
-    const int row = rbase + lane;
-    if (row < row_end) spart[row - row_begin] = v[0];
+    const int row = rbase + (lane & (RB - 1));
+    if (row < row_end && lane < RB) spart[row - row_begin] = v[0];
   };
   for (; r0 < row_end; r0 += 2 * kBatchStride) {
     process(r0, cwa);
@@ -430,7 +438,7 @@ __global__ void __launch_bounds__(kLutCThreads, 1) gemv_lut_cluster_kernel(const
     const int per = (nrows + p.n_slabs - 1) / p.n_slabs;
     const int lo = slab * per, hi = min(nrows, lo + per);
     const uint32_t sp = (uint32_t)__cvta_generic_to_shared(spart);
-    for (int r = lo + tid; r < hi; r += kLutCThreads) {
+    for (int r = lo + tid; r < hi; r += THREADS) {
       float acc = 0.f;
       for (int s2 = 0; s2 < p.n_slabs; ++s2) acc += ld_dsmem_f32(sp + 4u * (uint32_t)r, (uint32_t)s2);
       const int row = row_begin + r;

@@ -572,7 +572,9 @@ def run_ours(args):
                 from aqlm_b200.peer import PeerComm
 
                 peer_comm = PeerComm(max_elems=MODELS[model]["inter"] * 4)
-                reduce_kind = "fused peer-memory exchange + epilogue kernel (NVLink P2P stores, csrc/peer_allreduce.cuh)"
+                reduce_kind = ("exchange fused INTO the GEMV kernel over NVLink peer memory (P2P stores + per-CTA flags, csrc/gemv.cuh PEER)"
+                               if os.environ.get("AQLM_B200_FUSED_EXCHANGE", "1") != "0" else
+                               "partial GEMV + fused peer-memory exchange/epilogue kernel (csrc/peer_allreduce.cuh)")
             except Exception as e:
                 print(f"[bench] peer-memory communicator unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
                 peer_comm = None

@@ -196,7 +196,7 @@ def test_c_abi_grouped_and_comm_argument_checks_without_gpu():
     assert L.aqlm_b200_matmat_grouped(ctypes.byref(w), seg, 3, 16, 16, 9, 0, None) == _cabi.ERR_UNSUPPORTED
     # communicator sizing is pure arithmetic
     flag_bytes = 16 * 256 * 4  # flag[src rank (<=16)][CTA of the fused GEMV+exchange kernel (<=256)]
-    assert L.aqlm_b200_comm_shared_bytes(8, 1024) == flag_bytes + 2 * 8 * 1024 * 4
+    assert L.aqlm_b200_comm_shared_bytes(8, 1024) == flag_bytes + 2 * 8 * 1024 * (4 + 8)  # fp32 slots + tagged 64-bit words
     assert L.aqlm_b200_comm_shared_bytes(0, 1024) == 0 and L.aqlm_b200_comm_shared_bytes(17, 1024) == 0
     assert L.aqlm_b200_allreduce_scale_bias(None, None, None, None, None, 1, 4, 0, None) == _cabi.ERR_SHAPE
     assert L.aqlm_b200_matmat_allreduce(None, ctypes.byref(w), None, 1, 16, 16, 1, None) == _cabi.ERR_SHAPE

@@ -11,3 +11,9 @@ cat gpurun_out/probe_gemm_i*.jsonl
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_i.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_i.log
 tail -5 gpurun_out/pytest_gpu_i.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_i.log 2>&1; tail -3 gpurun_out/smoke_i.log
+# LUT cluster kernel, 16-row warp batches on 768 threads (side build)
+export AQLM_B200_LIB=$PWD/aqlm_b200/csrc/libaqlm_b200.so.rb16
+timeout 300 python tools/probe_lut.py 2>&1 | grep -E '"full"' > gpurun_out/probe_lut_i_rb32.jsonl
+AQLM_B200_LUT_RB16=1 timeout 300 python tools/probe_lut.py 2>&1 | grep -E '"full"' > gpurun_out/probe_lut_i_rb16.jsonl
+cat gpurun_out/probe_lut_i_rb32.jsonl gpurun_out/probe_lut_i_rb16.jsonl
+AQLM_B200_LUT_RB16=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "lut or kx8 or golden or schemes" 2>&1 | tail -3
