@@ -57,7 +57,7 @@ static int env_int(const char* name, int dflt) {
 // calls aqlm_b200_reload_tunables() after changing the environment.  Defaults are the shipped configuration.
 struct Tunables {
   int pdl, gemv_ctas_per_sm, gemv_threads, gather_mode, gemv_v2, force_generic;
-  int disable_lut, lut_ctas_per_sm, lut_debug, lut_cluster, lut_batch_loop, lut_rb16;
+  int disable_lut, lut_ctas_per_sm, lut_debug, lut_cluster, lut_batch_loop, lut_rb16, lut_c2_rb;
   int disable_tcgen05, gemm_stages, gemm_ksplit, gemm_cluster, gemm_debug, gemm_gather_mode, gemm_v2, gemm_tile_m, gemm_atmem, gemm_a_stages, gemm_groups;
   void load() {
     pdl = env_int("AQLM_B200_PDL", 1);
@@ -71,7 +71,8 @@ struct Tunables {
     lut_debug = env_int("AQLM_B200_LUT_DEBUG", 0);
     lut_batch_loop = env_int("AQLM_B200_LUT_BATCH_LOOP", 1);  // batch 2-3 on 256-entry codebooks: one LUT launch per row
     lut_rb16 = env_int("AQLM_B200_LUT_RB16", 0);  // cluster kernel: 16-row warp batches on 768 threads (experiment)
-    lut_cluster = env_int("AQLM_B200_LUT_CLUSTER", 1);  // K <= 2, in <= 4096: slab CTAs form a cluster, DSMEM reduction
+    lut_c2_rb = env_int("AQLM_B200_LUT_C2_RB", 0);  // cluster kernel, second form: rows per warp batch (0: by row-block size; 16; 32)
+    lut_cluster = env_int("AQLM_B200_LUT_CLUSTER", 2);  // K <= 2, in <= 4096: slab CTAs form a cluster, DSMEM reduction
     disable_tcgen05 = env_int("AQLM_B200_DISABLE_TCGEN05", 0);
     gemm_stages = env_int("AQLM_B200_GEMM_STAGES", 0);
     gemm_ksplit = env_int("AQLM_B200_GEMM_KSPLIT", 0);
@@ -425,6 +426,50 @@ static int lut_typed(const aqlm_b200_weight_t* w, const void* input, void* outpu
   }
 }
 
+// Second form of the cluster kernel (gemv_lut_cluster2_kernel): LUT at absolute shared address 0x10000, one warp per
+// row batch (the CTA size follows the row block), push-based cross-slab sum.
+template <typename T, int K, int RB, int MAXT = 1024>
+static int launch_lut_cluster2(const aqlm_b200_weight_t* w, const void* input, void* output, uint32_t flags,
+                               const DeviceInfo* di, cudaStream_t st, int rpb, int row_blocks, int n_slabs) {
+  int warps = (rpb + RB - 1) / RB;
+  warps = warps < 8 ? 8 : (warps > 32 ? 32 : warps);
+  if (MAXT == 1024 && warps <= 24)  // <= 768 threads: the 80-register build (the 64-register one spills ~50 words at RB = 32)
+    return launch_lut_cluster2<T, K, RB, 768>(w, input, output, flags, di, st, rpb, row_blocks, n_slabs);
+  auto kernel = gemv_lut_cluster2_kernel<T, K, RB, MAXT>;
+  const size_t smem = (size_t)kLutAbs + (size_t)K * 256 * kLutCJ * 4;  // LUT ends at 0x10000 * (1 + K) whatever the window base
+  static SmemMarks marks;
+  if (int rc = ensure_smem(kernel, smem, marks, di)) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = n_slabs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = tun().pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cfg.blockDim = dim3(warps * 32);
+  cfg.gridDim = dim3(n_slabs, row_blocks);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  LutClusterParams p;
+  p.codes = w->codes;
+  p.codebooks = w->codebooks;
+  p.scales = w->scales;
+  p.bias = w->bias;
+  p.x = input;
+  p.y = output;
+  p.out_features = (int)w->out_features;
+  p.in_groups = (int)(w->in_features / 8);
+  p.n_slabs = n_slabs;
+  p.rows_per_block = rpb;
+  p.partial_f32 = (flags & AQLM_B200_FLAG_PARTIAL_F32) ? 1 : 0;
+  AQLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
+  count_launch();
+  return AQLM_B200_OK;
+}
+
 // ---- Kx8 LUT GEMV, cluster / DSMEM variant (K <= 2, at most 8 slabs of 64 groups): host side ---------------
 template <typename T, int K, int RB, int THREADS>
 static int launch_lut_cluster(const aqlm_b200_weight_t* w, const void* input, void* output, uint32_t flags,
@@ -468,6 +513,13 @@ static int launch_lut_cluster(const aqlm_b200_weight_t* w, const void* input, vo
   rpb = (rpb + 31) / 32 * 32;
   if (rpb > 2048) return AQLM_B200_OK;  // per-row partials live in shared memory
   const int row_blocks = (int)((w->out_features + rpb - 1) / rpb);
+  if (tun().lut_cluster >= 2) {  // second form (default): same grid / cluster shape, its own CTA size and shared-memory map
+    const int rb_sel = tun().lut_c2_rb ? tun().lut_c2_rb : (rpb <= 512 ? 16 : 32);
+    const int rc = rb_sel == 16 ? launch_lut_cluster2<T, K, 16>(w, input, output, flags, di, st, rpb, row_blocks, n_slabs)
+                                : launch_lut_cluster2<T, K, 32>(w, input, output, flags, di, st, rpb, row_blocks, n_slabs);
+    *taken = rc == AQLM_B200_OK;
+    return rc;
+  }
   const size_t smem = lut_bytes + (size_t)rpb * 4;
   if (int rc = ensure_smem(kernel, smem, marks, di)) return rc;
   LutClusterParams p;

@@ -138,10 +138,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemv_vec_kernel(const GemvParams p
 #pragma unroll
         for (int e = 0; e < GPC; ++e) {
           const uint32_t code = chunk_code<CODE_BYTES>(cw, e);
+          if constexpr (!CBS && UPG == 2) {  // g = 16: the 32-byte entry is one 256-bit request
+            ld_gather_v8<GM>(gcb + (size_t)code * 2, wv[e][0], wv[e][1]);
+          } else {
 #pragma unroll
-          for (int h = 0; h < UPG; ++h) {
-            if constexpr (CBS) wv[e][h] = scb[code * UPG + h];
-            else wv[e][h] = ld_gather_v4<GM>(gcb + (size_t)code * UPG + h);
+            for (int h = 0; h < UPG; ++h) {
+              if constexpr (CBS) wv[e][h] = scb[code * UPG + h];
+              else wv[e][h] = ld_gather_v4<GM>(gcb + (size_t)code * UPG + h);
+            }
           }
         }
 #pragma unroll

@@ -455,4 +455,177 @@ __global__ void __launch_bounds__(THREADS, 1) gemv_lut_cluster_kernel(const LutC
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Cluster kernel, second form (default for K <= 2, in_features <= 8 slabs of 64 groups).  Same slab / lane <-> adjacent-group
+// layout and the same tensor-core LUT build as gemv_lut_cluster_kernel; three changes, each aimed at a measured cost
+// (profiles/r02/probe_lut_d.jsonl: lookups 2.9 us, cross-slab sum 1.6 us of an 8.9 us kernel at 2x8 4096->11008):
+//   * ONE instruction of address arithmetic per lookup.  The LUT is placed at the ABSOLUTE shared-memory address 0x10000
+//     (codebook k at 0x10000 * (1 + k)); a LUT row (one entry, 64 groups) is 256 bytes, so the address of entry `code` for
+//     the lane's group is  {byte3, byte2, byte1, byte0} = {0, 1 + k, code, 4 * lane}  -- one PRMT that takes the code byte
+//     straight out of the packed code word and the other three bytes from a per-lane constant; the lane's second (odd) group
+//     is the immediate offset +128 of the LDS.  (The first form spent SHL + LOP3 + IADD per lookup.)  The ~63 KiB below
+//     0x10000 are not wasted on this 1-CTA/SM kernel: they hold the receive buffers of the cross-slab sum.
+//   * every warp owns ONE batch of rows: the CTA is launched with as many warps as its row block has batches (<= 32), so
+//     there is no second, mostly empty, round (22 batches on 16 warps = 2 rounds before), and nothing is double-buffered
+//     (<= 64 registers).
+//   * the cross-slab sum is PUSH-based: a lane that ends the transpose-reduce with the slab total of a row stores it
+//     (st.shared::cluster) into the receive buffer of the CTA that owns the row's share; after ONE cluster barrier every CTA
+//     adds the n_slabs values of its rows from its OWN shared memory, in slab order (deterministic).  No remote loads, no
+//     second barrier (nobody touches a peer's memory after the barrier).
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kLutAbs = 0x10000u;  // absolute shared-memory address of LUT 0
+
+template <typename T, int K, int RB, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) gemv_lut_cluster2_kernel(const LutClusterParams p) {
+  static_assert(K == 1 || K == 2, "cluster LUT kernel: one or two 256-entry codebooks");
+  static_assert(RB == 32 || RB == 16, "rows per warp batch");
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  constexpr int J = kLutCJ, NT = J / 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_warps = (int)blockDim.x >> 5;
+  const int slab = blockIdx.x, rb = blockIdx.y;
+  const int j0 = slab * J;
+  griddep_launch_dependents();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // "I have started" (waited for before the pushes)
+  const uint32_t dyn_base = (uint32_t)__cvta_generic_to_shared(smem_dyn);
+  float* recv = reinterpret_cast<float*>(smem_dyn);                                 // [n_slabs][per], below the LUT
+  float* lut = reinterpret_cast<float*>(smem_dyn + (kLutAbs - dyn_base));           // [K][256][64] fp32 at 0x10000
+  const int row_begin = rb * p.rows_per_block;
+  const int row_end = min(p.out_features, row_begin + p.rows_per_block);
+  const int per = (p.rows_per_block + p.n_slabs - 1) / p.n_slabs;  // rows of a block that one CTA finishes
+  if (dyn_base + 4u * (uint32_t)(p.n_slabs * per) > kLutAbs) __trap();  // (host sizes the window; dyn_base is ~1 KiB)
+  const size_t row_bytes = (size_t)p.in_groups * K;
+  using CodeWord = typename std::conditional<K == 2, uint32_t, uint16_t>::type;
+  const bool g_ok = j0 + 2 * lane + 1 < p.in_groups;
+  const uint8_t* cbase = reinterpret_cast<const uint8_t*>(p.codes) + (size_t)(j0 + 2 * lane) * K;
+  const int batch_stride = n_warps * RB;
+  auto load_codes = [&](int r0, uint32_t (&cw)[RB]) {
+    const uint8_t* src = cbase + (size_t)r0 * row_bytes;
+    if (g_ok && r0 + RB <= row_end) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i, src += row_bytes) cw[i] = (uint32_t)__ldg(reinterpret_cast<const CodeWord*>(src));
+    } else {
+#pragma unroll
+      for (int i = 0; i < RB; ++i, src += row_bytes) {
+        cw[i] = 0u;
+        if (g_ok && r0 + i < row_end) cw[i] = (uint32_t)__ldg(reinterpret_cast<const CodeWord*>(src));
+      }
+    }
+  };
+  // ---- prologue (weights only; overlaps the previous kernel under PDL) ----
+  uint32_t cw[RB];
+  int r0 = row_begin + warp * RB;
+  if (r0 < row_end) load_codes(r0, cw);
+  const int q = lane >> 2, m = lane & 3;
+  const uint32_t* cb32 = reinterpret_cast<const uint32_t*>(p.codebooks);
+  uint32_t a0 = 0, a1 = 0;
+  if (warp < K * 16) {
+    a0 = __ldg(cb32 + (size_t)(warp * 16 + q) * 4 + m);
+    a1 = __ldg(cb32 + (size_t)(warp * 16 + q + 8) * 4 + m);
+  }
+  griddep_wait();  // x is produced by the previous kernel
+  // ---- LUT build (tensor cores), 16-entry tiles dealt to the warps ----
+  {
+    uint32_t bfrag[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int gg = j0 + 16 * (q >> 1) + 2 * t + (q & 1);
+      bfrag[t] = gg < p.in_groups ? reinterpret_cast<const uint32_t*>(p.x)[gg * 4 + m] : 0u;
+    }
+    for (int tile = warp; tile < K * 16; tile += n_warps) {
+      if (tile != warp) {
+        a0 = __ldg(cb32 + (size_t)(tile * 16 + q) * 4 + m);
+        a1 = __ldg(cb32 + (size_t)(tile * 16 + q + 8) * 4 + m);
+      }
+      const int e0 = tile * 16;
+      float* ra = lut + (size_t)(e0 + q) * J + 8 * m;
+      float* rb8 = lut + (size_t)(e0 + q + 8) * J + 8 * m;
+      const int odd = q & 1;  // odd entry rows store their second half first: a quarter-warp then covers all 32 banks
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // n-tiles 4h .. 4h+3 (two halves keep the accumulators at 16 registers)
+        float d[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          d[t][0] = d[t][1] = d[t][2] = d[t][3] = 0.f;
+          mma_m16n8k8(d[t], a0, a1, bfrag[4 * h + t], DT<T>::is_bf16);
+        }
+        const int off = (h ^ odd) * 4;
+        // accumulator column c: 0/1 = entry e0+q, even/odd groups; 2/3 = entry e0+q+8
+        *reinterpret_cast<float4*>(ra + off) = make_float4(d[0][0], d[1][0], d[2][0], d[3][0]);
+        *reinterpret_cast<float4*>(ra + 32 + off) = make_float4(d[0][1], d[1][1], d[2][1], d[3][1]);
+        *reinterpret_cast<float4*>(rb8 + off) = make_float4(d[0][2], d[1][2], d[2][2], d[3][2]);
+        *reinterpret_cast<float4*>(rb8 + 32 + off) = make_float4(d[0][3], d[1][3], d[2][3], d[3][3]);
+      }
+    }
+  }
+  __syncthreads();
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // every CTA of the cluster runs: its shared memory may be written
+  // ---- lookups: PRMT -> LDS -> FADD per code byte ----
+  const uint32_t c0 = kLutAbs | ((uint32_t)lane << 2);
+  const uint32_t c1 = (2u * kLutAbs) | ((uint32_t)lane << 2);
+  const uint32_t recv_s = dyn_base;
+  for (; r0 < row_end; r0 += batch_stride) {
+    if (r0 != row_begin + warp * RB) load_codes(r0, cw);  // (row blocks of more than 32 batches: later rounds, not prefetched)
+    float v[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const uint32_t w = cw[i];
+      float t0, t1, t2, t3;
+      if constexpr (K == 2) {  // bytes: [g0 k0][g0 k1][g1 k0][g1 k1]
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0) : "r"(__byte_perm(w, c0, 0x7604)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1) : "r"(__byte_perm(w, c1, 0x7614)));
+        asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(t2) : "r"(__byte_perm(w, c0, 0x7624)));
+        asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(t3) : "r"(__byte_perm(w, c1, 0x7634)));
+        v[i] = (t0 + t1) + (t2 + t3);
+      } else {                 // bytes: [g0][g1]
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0) : "r"(__byte_perm(w, c0, 0x7604)));
+        asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(t1) : "r"(__byte_perm(w, c0, 0x7614)));
+        v[i] = t0 + t1;
+      }
+    }
+    if constexpr (RB == 16) {  // 16 rows over 32 lanes: fold the two half-warps first, then transpose-reduce over 16 lanes
+#pragma unroll
+      for (int i = 0; i < RB; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+    }
+#pragma unroll
+    for (int dd = (RB == 32 ? 16 : 8), n = RB; dd >= 1; dd >>= 1, n >>= 1) {
+      const bool up = (lane & dd) != 0;
+#pragma unroll
+      for (int i = 0; i < n / 2; ++i) {
+        const float send = up ? v[i] : v[i + n / 2];
+        const float keep = up ? v[i + n / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, dd);
+      }
+    }
+    // lane (l & (RB-1)) holds the slab total of row r0 + (l & (RB-1)): push it to the CTA that finishes that row
+    const int rr = r0 - row_begin + (lane & (RB - 1));
+    if (lane < RB && r0 + (lane & (RB - 1)) < row_end) {
+      const int owner = rr / per;
+      const uint32_t local = recv_s + 4u * (uint32_t)(slab * per + (rr - owner * per));
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((uint32_t)owner));
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v[0]) : "memory");
+    }
+  }
+  // ---- cross-slab sum: everything I need has been pushed into MY shared memory once the cluster barrier completes ----
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  {
+    const int nrows = row_end - row_begin;
+    const int lo = slab * per, hi = min(nrows, lo + per);
+    for (int r = lo + tid; r < hi; r += (int)blockDim.x) {
+      float acc = 0.f;
+      for (int s2 = 0; s2 < p.n_slabs; ++s2) acc += *reinterpret_cast<volatile float*>(recv + s2 * per + (r - lo));
+      const int row = row_begin + r;
+      if (p.partial_f32) {
+        reinterpret_cast<float*>(p.y)[row] = acc;
+      } else {
+        const float sc = DT<T>::to_float(reinterpret_cast<const T*>(p.scales)[row]);
+        const float bi = p.bias ? DT<T>::to_float(reinterpret_cast<const T*>(p.bias)[row]) : 0.f;
+        reinterpret_cast<T*>(p.y)[row] = DT<T>::from_float(fmaf(acc, sc, bi));
+      }
+    }
+  }
+}
+
 }  // namespace aqlm_b200

@@ -572,7 +572,7 @@ def run_ours(args):
                 from aqlm_b200.peer import PeerComm
 
                 peer_comm = PeerComm(max_elems=MODELS[model]["inter"] * 4)
-                reduce_kind = ("exchange fused INTO the GEMV kernel over NVLink peer memory (P2P stores + per-CTA flags, csrc/gemv.cuh PEER)"
+                reduce_kind = ("exchange fused INTO the GEMV kernel over NVLink peer memory (tagged 64-bit {fp32, step} words pushed with P2P stores, LL-style: no fence/flag/barrier, csrc/gemv.cuh PEER)"
                                if os.environ.get("AQLM_B200_FUSED_EXCHANGE", "1") != "0" else
                                "partial GEMV + fused peer-memory exchange/epilogue kernel (csrc/peer_allreduce.cuh)")
             except Exception as e:
