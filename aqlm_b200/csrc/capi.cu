@@ -72,7 +72,7 @@ struct Tunables {
     lut_batch_loop = env_int("AQLM_B200_LUT_BATCH_LOOP", 1);  // batch 2-3 on 256-entry codebooks: one LUT launch per row
     lut_rb16 = env_int("AQLM_B200_LUT_RB16", 0);  // cluster kernel: 16-row warp batches on 768 threads (experiment)
     lut_c2_rb = env_int("AQLM_B200_LUT_C2_RB", 0);  // cluster kernel, second form: rows per warp batch (0: by row-block size; 16; 32)
-    lut_cluster = env_int("AQLM_B200_LUT_CLUSTER", 2);  // K <= 2, in <= 4096: slab CTAs form a cluster, DSMEM reduction
+    lut_cluster = env_int("AQLM_B200_LUT_CLUSTER", 1);  // K <= 2, in <= 4096: slab CTAs form a cluster, DSMEM reduction (2: second form, experimental)
     disable_tcgen05 = env_int("AQLM_B200_DISABLE_TCGEN05", 0);
     gemm_stages = env_int("AQLM_B200_GEMM_STAGES", 0);
     gemm_ksplit = env_int("AQLM_B200_GEMM_KSPLIT", 0);
@@ -261,7 +261,9 @@ static int dispatch_bt(const aqlm_b200_weight_t* w, const GemvParams& p, const D
       if (gm == 2) return launch_vec<T, 1, 2, 8, BT, false, 2>(p, di, st);
       return launch_vec<T, 1, 2, 8, BT, false, 0>(p, di, st);
     }
-    return launch_vec<T, 1, 2, 16, BT, false, 0>(p, di, st);
+    // g = 16: one codebook entry is fetched as ONE 256-bit request, which needs a 32-byte aligned table (any torch
+    // allocation is); a 16-byte aligned table handed in through the C-ABI takes the generic kernel below
+    if ((reinterpret_cast<uintptr_t>(w->codebooks) & 31) == 0) return launch_vec<T, 1, 2, 16, BT, false, 0>(p, di, st);
   }
   if (vec_ok && nbits == 8 && G == 8 && pow2k && need <= budget) {
     if (K == 1) return launch_vec<T, 1, 1, 8, BT, true, 0>(p, di, st);
@@ -513,7 +515,7 @@ static int launch_lut_cluster(const aqlm_b200_weight_t* w, const void* input, vo
   rpb = (rpb + 31) / 32 * 32;
   if (rpb > 2048) return AQLM_B200_OK;  // per-row partials live in shared memory
   const int row_blocks = (int)((w->out_features + rpb - 1) / rpb);
-  if (tun().lut_cluster >= 2) {  // second form (default): same grid / cluster shape, its own CTA size and shared-memory map
+  if (tun().lut_cluster >= 2) {  // second form (opt-in): same grid / cluster shape, its own CTA size and shared-memory map
     const int rb_sel = tun().lut_c2_rb ? tun().lut_c2_rb : (rpb <= 512 ? 16 : 32);
     const int rc = rb_sel == 16 ? launch_lut_cluster2<T, K, 16>(w, input, output, flags, di, st, rpb, row_blocks, n_slabs)
                                 : launch_lut_cluster2<T, K, 32>(w, input, output, flags, di, st, rpb, row_blocks, n_slabs);

@@ -460,9 +460,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemv_lut_cluster_kernel(const LutC
 // Cluster kernel, second form (default for K <= 2, in_features <= 8 slabs of 64 groups).  Same slab / lane <-> adjacent-group
 // layout and the same tensor-core LUT build as gemv_lut_cluster_kernel; three changes, each aimed at a measured cost
 // (profiles/r02/probe_lut_d.jsonl: lookups 2.9 us, cross-slab sum 1.6 us of an 8.9 us kernel at 2x8 4096->11008):
-//   * ONE instruction of address arithmetic per lookup.  The LUT is placed at the ABSOLUTE shared-memory address 0x10000
-//     (codebook k at 0x10000 * (1 + k)); a LUT row (one entry, 64 groups) is 256 bytes, so the address of entry `code` for
-//     the lane's group is  {byte3, byte2, byte1, byte0} = {0, 1 + k, code, 4 * lane}  -- one PRMT that takes the code byte
+//   * ONE instruction of address arithmetic per lookup.  The LUT is placed at the first 64 KiB boundary of the CTA's
+//     shared window above the receive buffers (window offset 0x10000; codebook k at 0x10000 * (1 + k)); a LUT row (one entry, 64 groups) is 256 bytes, so the address of entry `code` for
+//     the lane's group is  {byte3, byte2, byte1, byte0} = {base.hi, base.lo + k, code, 4 * lane}  -- one PRMT that takes the code byte
 //     straight out of the packed code word and the other three bytes from a per-lane constant; the lane's second (odd) group
 //     is the immediate offset +128 of the LDS.  (The first form spent SHL + LOP3 + IADD per lookup.)  The ~63 KiB below
 //     0x10000 are not wasted on this 1-CTA/SM kernel: they hold the receive buffers of the cross-slab sum.
@@ -488,13 +488,18 @@ __global__ void __launch_bounds__(MAXT, 1) gemv_lut_cluster2_kernel(const LutClu
   const int j0 = slab * J;
   griddep_launch_dependents();
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // "I have started" (waited for before the pushes)
+  // The shared-window address of this CTA's dynamic shared memory.  Only its low 16 bits are assumed small: inside a
+  // cluster the upper bits of a shared::cta address may carry the CTA's position in the shared::cluster window, so the LUT
+  // base is "the next 64 KiB boundary above the receive buffers", whatever those upper bits are.
   const uint32_t dyn_base = (uint32_t)__cvta_generic_to_shared(smem_dyn);
+  const uint32_t lut_base = (dyn_base & 0xffff0000u) + kLutAbs;                      // absolute address of LUT 0
   float* recv = reinterpret_cast<float*>(smem_dyn);                                 // [n_slabs][per], below the LUT
-  float* lut = reinterpret_cast<float*>(smem_dyn + (kLutAbs - dyn_base));           // [K][256][64] fp32 at 0x10000
+  float* lut = reinterpret_cast<float*>(smem_dyn + (lut_base - dyn_base));          // [K][256][64] fp32
   const int row_begin = rb * p.rows_per_block;
   const int row_end = min(p.out_features, row_begin + p.rows_per_block);
   const int per = (p.rows_per_block + p.n_slabs - 1) / p.n_slabs;  // rows of a block that one CTA finishes
-  if (dyn_base + 4u * (uint32_t)(p.n_slabs * per) > kLutAbs) __trap();  // (host sizes the window; dyn_base is ~1 KiB)
+  // (the host sizes the window as 64 KiB + the LUT; the dynamic area starts ~1 KiB into a 64 KiB-aligned window)
+  if ((dyn_base & 0xffffu) + 4u * (uint32_t)(p.n_slabs * per) > kLutAbs) __trap();
   const size_t row_bytes = (size_t)p.in_groups * K;
   using CodeWord = typename std::conditional<K == 2, uint32_t, uint16_t>::type;
   const bool g_ok = j0 + 2 * lane + 1 < p.in_groups;
@@ -541,16 +546,18 @@ __global__ void __launch_bounds__(MAXT, 1) gemv_lut_cluster2_kernel(const LutClu
       const int e0 = tile * 16;
       float* ra = lut + (size_t)(e0 + q) * J + 8 * m;
       float* rb8 = lut + (size_t)(e0 + q + 8) * J + 8 * m;
-      const int odd = q & 1;  // odd entry rows store their second half first: a quarter-warp then covers all 32 banks
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {  // n-tiles 4h .. 4h+3 (two halves keep the accumulators at 16 registers)
+      for (int h = 0; h < 2; ++h) {  // two passes of 4 n-tiles (keeps the accumulators at 16 registers).  Every lane of a
+                                     // pass holds the SAME half, so the even and the odd entry row of a quarter-warp store
+                                     // to the same banks (2-way conflict on the build stores; the first form avoids it by
+                                     // holding all 32 accumulators and letting odd rows store their second half first)
         float d[4][4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           d[t][0] = d[t][1] = d[t][2] = d[t][3] = 0.f;
           mma_m16n8k8(d[t], a0, a1, bfrag[4 * h + t], DT<T>::is_bf16);
         }
-        const int off = (h ^ odd) * 4;
+        const int off = h * 4;  // n-tiles 4h .. 4h+3 live at positions 8m + 4h + t
         // accumulator column c: 0/1 = entry e0+q, even/odd groups; 2/3 = entry e0+q+8
         *reinterpret_cast<float4*>(ra + off) = make_float4(d[0][0], d[1][0], d[2][0], d[3][0]);
         *reinterpret_cast<float4*>(ra + 32 + off) = make_float4(d[0][1], d[1][1], d[2][1], d[3][1]);
@@ -562,8 +569,8 @@ __global__ void __launch_bounds__(MAXT, 1) gemv_lut_cluster2_kernel(const LutClu
   __syncthreads();
   asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // every CTA of the cluster runs: its shared memory may be written
   // ---- lookups: PRMT -> LDS -> FADD per code byte ----
-  const uint32_t c0 = kLutAbs | ((uint32_t)lane << 2);
-  const uint32_t c1 = (2u * kLutAbs) | ((uint32_t)lane << 2);
+  const uint32_t c0 = lut_base | ((uint32_t)lane << 2);
+  const uint32_t c1 = (lut_base + kLutAbs) | ((uint32_t)lane << 2);
   const uint32_t recv_s = dyn_base;
   for (; r0 < row_end; r0 += batch_stride) {
     if (r0 != row_begin + warp * RB) load_codes(r0, cw);  // (row blocks of more than 32 batches: later rounds, not prefetched)

@@ -1,4 +1,5 @@
-"""2-GPU test of the fused peer-memory all-reduce + epilogue (skipped when fewer than 2 GPUs are visible)."""
+"""Multi-GPU exchange tests: the fused GEMV + peer exchange and the stand-alone exchange kernel on 2 GPUs (skipped when fewer
+are visible), and the same kernels on ONE GPU through a one-rank communicator (always runs)."""
 import os
 import socket
 
@@ -109,3 +110,86 @@ def test_one_process_two_devices_opt_in_shared_memory():
             y = op(t["x"], t["codes"], t["codebooks"], t["scales"], None)
             torch.cuda.synchronize(dev)
             assert c_oracle_check(t, y) < 5e-4, (dev, K, nbits, batch)
+
+
+def _self_exchange_worker(rank, port, ret):
+    """ONE GPU, one-rank communicator: the fused GEMV + exchange kernel pushes its tagged words into its OWN buffer and
+    waits for them there -- the same code path (contiguous row blocks, {fp32, step} words, set alternation, epilogue) as on
+    N GPUs, minus the NVLink hop, so the driver's single-GPU box exercises it too."""
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        from helpers import c_oracle_check, gpu_case, oracle_output, to_torch
+
+        from aqlm_b200 import _cabi
+        from aqlm_b200.grouped import ShardedQuantizedLinearGroup
+        from aqlm_b200.peer import PeerComm
+        from aqlm_b200.sharded import ShardedQuantizedLinear
+        from oracle import aqlm_oracle as O
+
+        comm = PeerComm(max_elems=4 * 28672)
+        errs = []
+
+        def shard(t):
+            m = ShardedQuantizedLinear.from_full(t["codes"], t["codebooks"], t["scales"], t.get("bias"), rank=0, world_size=1,
+                                                 peer_comm=comm)
+            m.world_size = 2  # take the exchange path; the communicator itself has one rank
+            return m
+
+        for it, (K, nbits, batch) in enumerate([(1, 16, 1), (1, 16, 3), (2, 8, 1), (1, 16, 8)]):
+            case = O.make_case(6150 + it, 2048, 520, K, nbits, 8, batch, bias=(it % 2 == 0))
+            t = to_torch(case, "cuda:0")
+            m = shard(t)
+            for fused in (True, False):
+                m.fused_exchange = fused
+                before = _cabi.launch_count()
+                for _ in range(3):  # odd number of steps: the two buffer sets alternate across linears as well
+                    y = m(t["x"])
+                torch.cuda.synchronize()
+                launches = (_cabi.launch_count() - before) // 3
+                if fused and (K, nbits) == (1, 16):
+                    assert launches == 1, launches  # GEMV + exchange + epilogue is ONE kernel
+                errs.append(O.relative_error(y.float().cpu().numpy(), oracle_output(case)))
+        # grouped q/k/v-like launch through the fused kernel
+        cases = [O.make_case(6300 + i, 2048, o, 1, 16, 8, 1, bias=False) for i, o in enumerate((512, 128, 128))]
+        for c in cases[1:]:
+            c["x"] = cases[0]["x"]
+        ms = [shard(to_torch(c, "cuda:0")) for c in cases]
+        grp = ShardedQuantizedLinearGroup(ms)
+        x = to_torch(cases[0], "cuda:0")["x"]
+        for _ in range(2):
+            ys = grp(x)
+        torch.cuda.synchronize()
+        for c, y in zip(cases, ys):
+            errs.append(O.relative_error(y.float().cpu().numpy(), oracle_output(c)))
+        # a Llama-3-70B 1/8 shard shape (down_proj: 28672/8 -> 8192) in a CUDA graph, against the C oracle
+        t = gpu_case(3584, 8192, 1, 16, 1, seed=78, device="cuda:0")
+        m = shard(t)
+        y = m(t["x"])
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = m(t["x"])
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        errs.append(c_oracle_check(t, y))
+        ret[0] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_exchange_kernel_on_one_gpu_self_communicator():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_self_exchange_worker, args=(port, ret), nprocs=1, join=True)
+    assert len(ret[0]) == 12 and all(e < 5e-4 for e in ret[0]), ret[0]
