@@ -1,4 +1,4 @@
-"""Cluster LUT GEMV, first vs second form (AQLM_B200_LUT_CLUSTER=1|2, AQLM_B200_LUT_C2_RB=0|16|32): time per launch
+"""Cluster LUT GEMV, first vs second form (AQLM_B200_LUT_CLUSTER=1|2|3, AQLM_B200_LUT_C2_RB=0|16|32): time per launch
 (CUDA-graph replay over rotating weight copies, CUDA events) and a parity check of every variant against the fp32
 dequantized matvec computed by torch on the same tensors."""
 import json
@@ -27,7 +27,8 @@ def dense_ref(x, codes, codebooks, scales):
 def main():
     dev = "cuda:0"
     shapes = ((2, (4096, 11008)), (2, (4096, 4096)), (1, (4096, 11008)), (2, (4096, 22016)), (2, (4096, 12288)), (2, (1024, 4096)), (1, (4096, 4096)))
-    variants = (("first form", {"AQLM_B200_LUT_CLUSTER": "1"}),
+    variants = (("shipped default (second form up to 640-row blocks, first form above)", {}),
+                ("first form", {"AQLM_B200_LUT_CLUSTER": "1"}),
                 ("second form, auto", {"AQLM_B200_LUT_CLUSTER": "2"}),
                 ("second form, RB16", {"AQLM_B200_LUT_CLUSTER": "2", "AQLM_B200_LUT_C2_RB": "16"}),
                 ("second form, RB32", {"AQLM_B200_LUT_CLUSTER": "2", "AQLM_B200_LUT_C2_RB": "32"}))
