@@ -176,6 +176,31 @@ def import_reference_aqlm():
     return aqlm
 
 
+def host_threads():
+    """Threads for the CPU legs: the physical cores this process may run on (torch's own default when OMP_NUM_THREADS is
+    unset).  torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently turn the N > 1 reference arm into a
+    single-thread run; the reference arm is meant to use the host cores it can (AQLM_BENCH_CPU_THREADS overrides)."""
+    forced = int(os.environ.get("AQLM_BENCH_CPU_THREADS", "0") or 0)
+    if forced > 0:
+        return forced
+    try:
+        logical = len(os.sched_getaffinity(0))
+    except AttributeError:
+        logical = os.cpu_count() or 1
+    physical = set()
+    try:
+        phys = "0"
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("physical id"):
+                    phys = ln.split(":", 1)[1].strip()
+                elif ln.startswith("core id"):
+                    physical.add((phys, ln.split(":", 1)[1].strip()))
+    except OSError:
+        pass
+    return max(1, min(logical, len(physical) or logical))
+
+
 def cpu_reference_layer_sample(model, K, nbits, target_seconds, numba_threads=1):
     """Time the reference's own `QuantizedLinear.forward` on CPU (inference_lib/src/aqlm/inference.py:68-75) on ONE decoder
     layer's 7 linears, bs=1, fp32 (the dtype of benchmark/matmul_benchmark_cpu.py:114-123).  1x16 resolves to
@@ -194,6 +219,8 @@ def cpu_reference_layer_sample(model, K, nbits, target_seconds, numba_threads=1)
         return None
     import torch
 
+    if not lut and torch.get_num_threads() < host_threads():
+        torch.set_num_threads(host_threads())  # e.g. under torchrun, which sets OMP_NUM_THREADS=1 for its workers
     torch.manual_seed(0)
     lo, hi = (-128, 128) if nbits <= 8 else (-(2 ** (nbits - 1)), 2 ** (nbits - 1))
     mods = []
