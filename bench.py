@@ -62,6 +62,37 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+class Watchdog:
+    """N > 1 only: the fused exchange makes kernels of one rank wait for kernels of the others; if a rank never arrives (a bug,
+    a dead peer), that wait would spin until the driver's own limit.  The watchdog ends the process instead: it prints which
+    phase was stuck (rank 0: as a JSON line on stdout) and leaves through os._exit, which tears the CUDA context down and
+    with it the spinning kernel.  Armed per phase; `phase()` re-arms it."""
+
+    def __init__(self, rank, seconds, enabled=True):
+        self.rank, self.seconds, self.enabled = rank, float(seconds), enabled and seconds > 0
+        self.name, self.timer = "start", None
+
+    def _fire(self):
+        msg = {"error": f"watchdog: phase '{self.name}' did not finish within {self.seconds:.0f} s", "rank": self.rank}
+        print(f"[bench] {json.dumps(msg)}", file=sys.stderr, flush=True)
+        if self.rank == 0:
+            print(json.dumps(msg), flush=True)
+        os._exit(5)
+
+    def phase(self, name):
+        self.cancel()
+        self.name = name
+        if self.enabled:
+            self.timer = threading.Timer(self.seconds, self._fire)
+            self.timer.daemon = True
+            self.timer.start()
+
+    def cancel(self):
+        if self.timer is not None:
+            self.timer.cancel()
+            self.timer = None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -591,6 +622,8 @@ def run_ours(args):
     total_bytes = model_code_bytes(model, K, nbits, n_layers)
     peak, peak_src = measured_peaks()
 
+    wd = Watchdog(rank, args.watchdog_seconds, enabled=world > 1)
+    wd.phase("communicator setup")
     peer_comm, reduce_kind = None, "none"
     if world > 1:
         reduce_kind = "nccl all-reduce + epilogue kernel"
@@ -607,6 +640,7 @@ def run_ours(args):
                 peer_comm = None
     parity = None
     if world > 1 and not args.skip_parity:
+        wd.phase("sharded_parity (first use of the exchange at this N)")
         parity = sharded_parity(model, K, nbits, device, rank, world, peer_comm)
         if parity["max_rel"] > parity["tolerance"]:
             if rank == 0:
@@ -614,6 +648,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             dist.barrier()
             os._exit(3)
+    wd.phase("model build, first steps, graph capture")
     layers = build_model(model, K, nbits, n_layers, device, rank, world, peer_comm)
     grouped = not args.no_group and (K, nbits) == (1, 16)
     if grouped:
@@ -670,6 +705,7 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    wd.phase("warm-up and timed steps")
     for _ in range(max(3, args.warmup)):
         run()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -696,6 +732,7 @@ def run_ours(args):
     # ---- N > 1, reported beside the headline: the Megatron-style pairing --------------------------
     # q/k/v and gate/up sharded along OUT_features (each rank owns rows, no exchange: their consumers are sharded the same
     # way), o_proj and down_proj sharded along in_features with ONE exchange each: 2 exchanges per layer instead of 4.
+    wd.phase("pairing variant / same-workload single-GPU point")
     pairing = None
     if world > 1 and (K, nbits) == (1, 16) and not args.skip_pairing:
         try:
@@ -790,6 +827,7 @@ def run_ours(args):
             same_n1 = {"error": f"{type(e).__name__}: {e}"}
     if world > 1:
         dist.barrier()
+    wd.cancel()
 
     if rank == 0:
         value = total_bytes / (ms_step * 1e-3) / 1e9
@@ -896,6 +934,8 @@ def main():
     ap.add_argument("--skip-pairing", action="store_true", help="N>1: skip the out/in-features pairing variant")
     ap.add_argument("--skip-parity", action="store_true", help="N>1: skip the sharded-vs-unsharded correctness pass")
     ap.add_argument("--skip-reference-gpu", action="store_true", help="skip the reference CUDA kernels / generate legs")
+    ap.add_argument("--watchdog-seconds", type=float, default=420.0,
+                    help="N>1: leave with an error line if one phase (parity, build, timing, ...) takes longer than this (0: off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
