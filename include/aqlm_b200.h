@@ -143,11 +143,14 @@ int aqlm_b200_allreduce_scale_bias(aqlm_b200_comm* comm, const float* partial, c
                                    void* output, int64_t batch, int64_t out_features, int32_t dtype, void* stream);
 
 /* The sharded linear as ONE kernel (1x16, in_group 8, batch <= 8): fused code-gather + dequant + GEMV on this rank's
- * in_features shard whose reduction epilogue pushes the fp32 partials to every peer over NVLink (contiguous row blocks,
- * 16-byte P2P stores), signals / waits per CTA, adds the W partial vectors in rank order and applies scale + bias.  `w`
- * describes the SHARD (in_features = local slice) with full-length scales/bias; `seg_rows`/`n_seg` as in
- * aqlm_b200_matmat_grouped (n_seg == 1: a plain linear, seg_rows may be NULL).  Every rank must call it the same number
- * of times in the same order (it shares the step counter with aqlm_b200_allreduce_scale_bias). */
+ * in_features shard whose reduction epilogue performs the exchange over NVLink peer memory: every (row, batch) element
+ * travels as one tagged 64-bit word {fp32 partial, step} stored into slot [step & 1][this rank] of EVERY rank's buffer
+ * (8-byte P2P stores, coalesced per warp); the same thread then polls the W words of that element in its OWN buffer until
+ * their tags equal the step, adds them in rank order (deterministic) and applies scale + bias -- no fence, flag or barrier
+ * between push and reduction.  `w` describes the SHARD (in_features = local slice) with full-length scales/bias;
+ * `seg_rows`/`n_seg` as in aqlm_b200_matmat_grouped (n_seg == 1: a plain linear, seg_rows may be NULL).  Every rank must
+ * call it the same number of times in the same order (it shares the step counter with aqlm_b200_allreduce_scale_bias);
+ * the grid is one CTA per SM so that all ranks' CTAs are resident while they wait for each other. */
 int aqlm_b200_matmat_allreduce(aqlm_b200_comm* comm, const aqlm_b200_weight_t* w, const int64_t* seg_rows, int n_seg,
                                const void* input, void* output, int64_t batch, void* stream);
 
