@@ -732,6 +732,54 @@ def run_ours(args):
     # ---- N > 1, reported beside the headline: the Megatron-style pairing --------------------------
     # q/k/v and gate/up sharded along OUT_features (each rank owns rows, no exchange: their consumers are sharded the same
     # way), o_proj and down_proj sharded along in_features with ONE exchange each: 2 exchanges per layer instead of 4.
+    # ---- N > 1: compute vs exchange split.  The exchange lives inside the GEMV kernel, so the split is measured
+    # by difference: the same step with every linear's GEMV writing its UNSCALED fp32 partials and no exchange at all
+    # (matmat_partial / the grouped partial launch).  Local to each rank (no collective in this leg: a rank-local failure
+    # cannot strand the others); rank 0 reports its own clock.
+    compute_only = None
+    if world > 1:
+        wd.phase("compute-only step (no exchange)")
+        try:
+            from aqlm_b200.grouped import ShardedQuantizedLinearGroup as _SGroup
+            from aqlm_b200.inference_kernels import cuda_kernel as _ck
+
+            def cstep():
+                for mods in layers:
+                    for m, n in mods:
+                        if isinstance(m, _SGroup):
+                            _ck.matmat_grouped(x_dev[n], m._fused_codes, m._fused_codebooks, None, None, m.seg_rows, partial=True)
+                        else:
+                            _ck.matmat_partial(x_dev[n], m.codes, m.codebooks)
+
+            cstep()
+            torch.cuda.synchronize()
+            gc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gc):
+                cstep()
+            for _ in range(3):
+                gc.replay()
+            torch.cuda.synchronize()
+            n_it = max(5, args.steps // 2)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(n_it):
+                gc.replay()
+            ev1.record()
+            torch.cuda.synchronize()
+            ms_c = ev0.elapsed_time(ev1) / n_it
+            compute_only = {"ms_per_step_compute_only": ms_c, "ms_per_step_with_exchange": ms_step,
+                            "exchange_share_of_step": max(0.0, 1.0 - ms_c / ms_step),
+                            "compute_only_value": total_bytes / (ms_c * 1e-3) / 1e9, "unit": "GB/s",
+                            "note": "same sharded step, every GEMV writing unscaled fp32 partials, no exchange; rank 0's clock"}
+            gc.reset()
+            del gc
+        except Exception as e:
+            compute_only = {"error": f"{type(e).__name__}: {e}"}
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+
     wd.phase("pairing variant / same-workload single-GPU point")
     pairing = None
     if world > 1 and (K, nbits) == (1, 16) and not args.skip_pairing:
@@ -889,6 +937,8 @@ def run_ours(args):
             line["sharded_parity"] = parity
         if pairing is not None:
             line["tp_pairing_variant"] = pairing
+        if compute_only is not None:
+            line["compute_vs_exchange"] = compute_only
         print(json.dumps(line), flush=True)
     if world > 1:
         # Clean teardown: drop the CUDA graphs (they may hold captured NCCL kernels), sync, then destroy the process group.
