@@ -960,11 +960,11 @@ def run_ours(args):
             print("[bench] destroy_process_group did not return within 20 s; leaving through os._exit", file=sys.stderr, flush=True)
             os._exit(0)
 
-        wd = threading.Timer(20.0, _bail)
-        wd.daemon = True
-        wd.start()
+        teardown_timer = threading.Timer(20.0, _bail)
+        teardown_timer.daemon = True
+        teardown_timer.start()
         dist.destroy_process_group()
-        wd.cancel()
+        teardown_timer.cancel()
 
 
 def main():
