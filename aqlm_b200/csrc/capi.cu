@@ -73,9 +73,11 @@ struct Tunables {
     lut_rb16 = env_int("AQLM_B200_LUT_RB16", 0);  // cluster kernel: 16-row warp batches on 768 threads (experiment)
     lut_c2_rb = env_int("AQLM_B200_LUT_C2_RB", 0);  // cluster kernel, second form: rows per warp batch (0: by row-block size; 16; 32)
     // K <= 2, in <= 4096: slab CTAs form a cluster, DSMEM reduction.  0: off (workspace kernel), 1: first form, 2: second form,
-    // 3 (default): second form for row blocks of <= 704 rows (Llama-2-7B: 4096 -> 4096 / 11008, whose row blocks are
-    // 256 and 640-704 rows on 16-18 resident clusters), first form above (measured, profiles/r02/probe_lut2_n.jsonl:
-    // second form +12..+27 % up to 11008 rows, -2..-4 % at 12288 / 22016 rows = blocks of >= 736 rows)
+    // 3 (default): second form for row blocks of <= 768 rows = at most 24 warps of 32 rows, the 768-thread / 80-register
+    // build (Llama-2-7B: 4096 -> 4096 / 11008; 15 clusters of 8 CTAs were resident on the measured boxes, i.e. blocks of
+    // 288 and 736 rows), first form above, where the second form needs its 1024-thread / 64-register build and spills
+    // (measured, profiles/r02/probe_lut2_n.jsonl: second form +12..+27 % up to 11008 rows, -2..-4 % at 12288 / 22016
+    // rows = blocks of 832 / 1472 rows)
     lut_cluster = env_int("AQLM_B200_LUT_CLUSTER", 3);
     disable_tcgen05 = env_int("AQLM_B200_DISABLE_TCGEN05", 0);
     gemm_stages = env_int("AQLM_B200_GEMM_STAGES", 0);
@@ -519,7 +521,7 @@ static int launch_lut_cluster(const aqlm_b200_weight_t* w, const void* input, vo
   rpb = (rpb + 31) / 32 * 32;
   if (rpb > 2048) return AQLM_B200_OK;  // per-row partials live in shared memory
   const int row_blocks = (int)((w->out_features + rpb - 1) / rpb);
-  if (tun().lut_cluster == 2 || (tun().lut_cluster >= 3 && rpb <= 704)) {  // second form: same grid / cluster shape, its own CTA size and shared-memory map
+  if (tun().lut_cluster == 2 || (tun().lut_cluster >= 3 && rpb <= 768)) {  // second form: same grid / cluster shape, its own CTA size and shared-memory map
     const int rb_sel = tun().lut_c2_rb ? tun().lut_c2_rb : (rpb <= 512 ? 16 : 32);
     const int rc = rb_sel == 16 ? launch_lut_cluster2<T, K, 16>(w, input, output, flags, di, st, rpb, row_blocks, n_slabs)
                                 : launch_lut_cluster2<T, K, 32>(w, input, output, flags, di, st, rpb, row_blocks, n_slabs);
