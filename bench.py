@@ -542,8 +542,10 @@ def secondary_metrics(device, peak_hbm, args):
                 x = torch.randn((bs, fin), dtype=dt, device=device)
                 us = timed([(lambda w=w: cuda_kernel.matmat_dequant(x, w[0], w[1], w[2], None)) for w in ws])
                 tf = 2.0 * bs * fin * fout / us / 1e6
+                cgb = code_bytes(fin, fout, 1, 16) / us / 1e3  # small batches are gather/HBM-bound -- report both
                 out["gemm"].append({"shape": f"{fin}x{fout}", "scheme": "1x16", "batch": bs, "operands": name, "us": round(us, 2),
-                                    "tflops": round(tf, 1), "frac_of_measured_bf16_peak": round(tf / tpeak, 4)})
+                                    "tflops": round(tf, 1), "frac_of_measured_bf16_peak": round(tf / tpeak, 4),
+                                    "code_GBps": round(cgb, 1), "frac_of_hbm_peak": round(cgb / peak_hbm, 4)})
             del ws
     # backward op (fused dequant-transpose GEMM): grad_in[bs, in] = (grad_out * scales) @ W
     try:
